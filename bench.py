@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the fused view-synthesis loss (forward + backward) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): warped pixels per second of the fused loss forward+backward, where a
+warped pixel is one (image, scale, source frame, y, x) sample: B * S * scales * H * W per step.
+Workload at every N: BASELINE.json configs[1] per GPU - batch 12, 192x640, frame_ids [0,-1,1]
+(S=2), 4 scales, fp32, auto-mask on, synthetic i.i.d. U(0,1) images (weak scaling: every rank
+runs its own batch; the path has no data-path collective).
+
+A step is one pass of the hot path over one batch:
+  value    the three launches of md2_loss_forward_backward through the C ABI, inputs resident in
+           HBM.  The step rotates over several independent input/output sets whose total size
+           exceeds the 126 MB L2, so no step finds its inputs cached.
+  e2e      the same step through the public Python API (md2_b200.compute: image2warping +
+           compute_loss + loss.backward()) with HOST inputs: every step copies the batch from
+           pinned host memory and reads the loss back.
+  roofline the tile kernel alone (CUDA events recorded around it on its stream), algorithmic
+           bytes N*(183.8125 + 112*S) against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the oracle port of the reference's PyTorch path on the host cores, bounded sample.
+
+--impl reference times that CPU port (oracle/oracle_torch.py) as the reference arm: the reference is
+Python and cannot travel to the GPU box (it is not copied into this repo); the port is pinned to the
+reference's own outputs by tests/test_oracle_golden.py.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B, H, W, FRAME_IDS, NUM_SCALES = 12, 192, 640, [0, -1, 1], 4
+S = len(FRAME_IDS) - 1
+METRIC = "warped_pixels_per_sec_fused_loss_fwd_bwd"
+UNIT = "warped_px/s"
+WORKLOAD = "fused view-synthesis loss fwd+bwd, batch 12 per GPU, 192x640, frame_ids [0,-1,1], 4 scales, automask, fp32"
+
+
+def algorithmic_bytes(b, h, w, s):
+    return b * h * w * (183.8125 + 112.0 * s)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([x.strip() for x in o.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_host_batch(seed):
+    """One synthetic batch on the host, shaped like the reference loaders' output."""
+    import md2_b200.synthetic as syn
+    from oracle.oracle_torch import pose_matrix  # only to build pose matrices for the synthetic batch
+    inputs, outputs = syn.make_batch(B, H, W, FRAME_IDS, NUM_SCALES, seed, "iid", requires_grad=False)
+    for f in FRAME_IDS[1:]:
+        outputs[("c2c", f, 0)] = pose_matrix(outputs[("axisangle", f)], outputs[("translation", f)],
+                                             invert=(f < 0)).detach()
+    return inputs, outputs
+
+
+def to_args(inputs, outputs, dev):
+    g = lambda t: t.to(dev, non_blocking=True)
+    srcs = FRAME_IDS[1:]
+    return dict(target=g(inputs[("color", 0, 0)]), sources=[g(inputs[("color", f, 0)]) for f in srcs],
+                disps=[g(outputs[("disp", s)]) for s in range(NUM_SCALES)],
+                color_pyr=[g(inputs[("color", 0, s)]) for s in range(NUM_SCALES)],
+                K=g(inputs[("K", 0)]), inv_K=g(inputs[("inv_K", 0)]),
+                Ts=[g(outputs[("c2c", f, 0)]) for f in srcs], automask=True, noise=None)
+
+
+# ------------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import ctypes as C
+    import torch.distributed as dist
+    import md2_b200.cabi as cabi
+    from md2_b200.compute import compute as FusedCompute
+    from types import SimpleNamespace
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours): no CUDA device - the fused loss has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cl = cabi.CLoss()
+    lib = cl.lib
+    # ---- device-resident leg: rotating sets larger than L2 -------------------------------------
+    n_sets = 3
+    host = [make_host_batch(100 * rank + i) for i in range(n_sets)]
+    sets = []
+    set_bytes = 0
+    for inputs, outputs in host:
+        a = to_args(inputs, outputs, dev)
+        a["seed"] = 1
+        prep, cfg, inp = cl._prep(a)
+        o = cl._alloc_out(cfg, dev)
+        gd = [torch.empty_like(d) for d in prep["disps"]]
+        gT = [torch.empty(B, 4, 4, device=dev) for _ in prep["Ts"]]
+        ws = cl._ws(cfg, dev)
+        out = cabi.make_outputs(o["loss"], None, o["argmin"], o["depth"])
+        g = cabi.make_grads(gd, gT)
+        sets.append((prep, cfg, inp, out, g, ws, o, gd, gT))
+        tens = [prep["target"]] + prep["sources"] + prep["disps"] + prep["color_pyr"][1:] + \
+               [o["argmin"], o["depth"]] + gd
+        set_bytes = sum(t.numel() * t.element_size() for t in tens)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def step(i):
+        prep, cfg, inp, out, g, ws, *_ = sets[i % n_sets]
+        rc = lib.md2_loss_forward_backward(C.byref(cfg), C.byref(inp), C.byref(out), C.byref(g), C.c_float(1.0),
+                                           C.c_void_p(ws.data_ptr()), stream)
+        if rc != 0:
+            raise RuntimeError(f"md2_loss_forward_backward returned {rc}")
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = clk.summary()
+
+    # ---- tile kernel alone (roofline leg): events recorded around the launch on its stream ------
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(); k1.record()  # materialise the cudaEvent_t handles
+    torch.cuda.synchronize()
+    lib.md2_set_tile_kernel_events(C.c_void_p(k0.cuda_event), C.c_void_p(k1.cuda_event))
+    kms = []
+    for i in range(min(args.steps, 20)):
+        step(i)
+        torch.cuda.synchronize()
+        kms.append(k0.elapsed_time(k1))
+    lib.md2_set_tile_kernel_events(None, None)
+    kernel_ms = sum(kms) / len(kms)
+
+    # ---- end-to-end leg: public API, host inputs in pinned memory -------------------------------
+    opt = SimpleNamespace(frame_ids=FRAME_IDS, scales=range(NUM_SCALES), height=H, width=W, min_depth=0.1,
+                          max_depth=100.0, pose_type="separate", use_automasking=True, disp_smoothness=1e-3)
+    comp = FusedCompute(opt, dev)
+    pinned = []
+    for inputs, outputs in host:
+        pin_in = {k: v.pin_memory() for k, v in inputs.items()}
+        pin_out = {k: v.pin_memory() for k, v in outputs.items() if k[0] in ("disp", "c2c")}
+        pinned.append((pin_in, pin_out))
+    h2d_bytes = sum(v.numel() * v.element_size() for d in pinned[0] for v in d.values())
+    loss_host = torch.empty((), pin_memory=True)
+
+    def e2e_step(i):
+        pin_in, pin_out = pinned[i % n_sets]
+        inputs = {k: v.to(dev, non_blocking=True) for k, v in pin_in.items()}
+        outputs = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in pin_out.items()}
+        comp.image2warping(inputs, outputs, None)
+        comp.compute_loss(inputs, outputs, None)
+        outputs["loss"].backward()
+        loss_host.copy_(outputs["loss"].detach(), non_blocking=True)
+        return outputs
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    x1.record()
+    barrier()
+    e2e_ms_total = x0.elapsed_time(x1)
+
+    # ---- max over ranks -------------------------------------------------------------------------
+    t = torch.tensor([ms_total, e2e_ms_total, kernel_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_total, kernel_ms = [float(x) for x in t.tolist()]
+    px_step = B * S * NUM_SCALES * H * W * world
+    value = px_step * args.steps / (ms_total * 1e-3)
+    e2e_value = px_step * args.steps / (e2e_ms_total * 1e-3)
+    peak, peak_src = hbm_peak()
+    algo = algorithmic_bytes(B, H, W, S)
+    achieved = algo / (kernel_ms * 1e-3) / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "height": H, "width": W, "sources": S,
+                   "scales": NUM_SCALES, "warped_px_per_step": px_step,
+                   "l2": f"rotating {n_sets} independent input/output sets of {set_bytes / 1e6:.0f} MB each "
+                         f"({n_sets * set_bytes / 1e6:.0f} MB > 126 MB L2)",
+                   "noise": "auto-mask noise generated on the device (statistically equivalent to the "
+                            "reference's host torch.randn)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms_total / args.steps,
+                "api": "md2_b200.compute.compute.image2warping + compute_loss + loss.backward(), pinned host inputs"},
+        "gpu_launches": 3 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "md2::tile_kernel<Tile<2,true,32,16,256>>",
+                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo, "peak_source": peak_src},
+    }
+    if rank == 0:
+        line["cpu_baseline"] = cpu_baseline(steps=3)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ CPU port
+CPU_B = 4  # bounded sample: one third of the batch (same image size, sources and scales)
+
+
+def cpu_step_fn():
+    from oracle import oracle_torch as O
+    import md2_b200.synthetic as syn
+    torch.set_num_threads(os.cpu_count() or 1)
+    inputs, outputs = syn.make_batch(CPU_B, H, W, FRAME_IDS, NUM_SCALES, 0, "iid", requires_grad=False)
+    srcs = FRAME_IDS[1:]
+    Ts = [O.pose_matrix(outputs[("axisangle", f)], outputs[("translation", f)], invert=(f < 0)).detach()
+          for f in srcs]
+    base = dict(target=inputs[("color", 0, 0)], sources=[inputs[("color", f, 0)] for f in srcs],
+                color_pyr=[inputs[("color", 0, s)] for s in range(NUM_SCALES)], K=inputs[("K", 0)],
+                inv_K=inputs[("inv_K", 0)], automask=True, noise=None)
+
+    def step():
+        disps = [outputs[("disp", s)].clone().requires_grad_(True) for s in range(NUM_SCALES)]
+        T = [t.clone().requires_grad_(True) for t in Ts]
+        out = O.view_synthesis_loss(disps=disps, Ts=T, **base)
+        out["loss"].backward()
+        return float(out["loss"])
+    return step
+
+
+def cpu_baseline(steps=3):
+    step = cpu_step_fn()
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    px = CPU_B * S * NUM_SCALES * H * W
+    return {"value": px / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps of batch {CPU_B} (of 12) at 192x640, S=2, 4 scales, fwd+bwd, "
+                      f"oracle/oracle_torch.py on the host CPU, {dt:.3f} s/step"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step = cpu_step_fn()
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    px = CPU_B * S * NUM_SCALES * H * W
+    value = px * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = (f"each step = batch {CPU_B} (of 12) at 192x640, S=2, 4 scales, fwd+bwd on {cores} host threads; "
+              f"px/s is size-independent per image")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

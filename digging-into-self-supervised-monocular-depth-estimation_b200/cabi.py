@@ -48,7 +48,7 @@ class md2_grads(C.Structure):
 # every symbol include/md2_loss.h declares
 EXPORTS = ["md2_workspace_bytes", "md2_loss_forward", "md2_loss_forward_backward",
            "md2_loss_backward", "md2_pose_forward", "md2_pose_backward",
-           "md2_launches_per_step", "md2_version", "md2_debug_warp"]
+           "md2_launches_per_step", "md2_version", "md2_debug_warp", "md2_set_tile_kernel_events"]
 
 LIB_NAME = "libmd2loss.so"
 
@@ -86,6 +86,8 @@ def load_library(path=None):
     lib.md2_launches_per_step.argtypes = [C.POINTER(md2_cfg), C.c_int]
     lib.md2_version.restype = C.c_char_p
     lib.md2_version.argtypes = []
+    lib.md2_set_tile_kernel_events.restype = None
+    lib.md2_set_tile_kernel_events.argtypes = [C.c_void_p, C.c_void_p]
     lib.md2_debug_warp.restype = C.c_int
     lib.md2_debug_warp.argtypes = [C.POINTER(md2_cfg), C.POINTER(md2_inputs), C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -139,3 +141,104 @@ def make_grads(grad_disp, grad_T):
     for i, t in enumerate(grad_T):
         g.grad_T[i] = t.data_ptr() if t is not None else None
     return g
+
+
+class CLoss:
+    """Thin convenience wrapper used by the GPU parity tests: calls the C ABI of
+    libmd2loss.so with raw device pointers of torch CUDA tensors on the current stream."""
+
+    def __init__(self, path=None):
+        self.lib = load_library(path)
+
+    @staticmethod
+    def _prep(args):
+        import torch
+        f = lambda t: t.detach().to(torch.float32).contiguous()
+        a = dict(target=f(args["target"]), sources=[f(t) for t in args["sources"]],
+                 disps=[f(t) for t in args["disps"]], color_pyr=[f(t) for t in args["color_pyr"]],
+                 K=f(args["K"]), inv_K=f(args["inv_K"]), Ts=[f(t) for t in args["Ts"]],
+                 noise=[f(t) for t in args["noise"]] if args.get("noise") is not None else None)
+        B, _, H, W = a["target"].shape
+        cfg = make_cfg(B, H, W, len(a["sources"]), len(a["disps"]), args.get("automask", True),
+                       args.get("min_depth", 0.1), args.get("max_depth", 100.0),
+                       args.get("disp_smoothness", 1e-3))
+        inp = make_inputs(a["target"], a["sources"], a["disps"], a["color_pyr"], a["K"], a["inv_K"],
+                          a["Ts"], a["noise"], args.get("seed", 0))
+        return a, cfg, inp
+
+    def _ws(self, cfg, dev):
+        import torch
+        n = self.lib.md2_workspace_bytes(C.byref(cfg))
+        assert n > 0
+        return torch.empty(n, dtype=torch.uint8, device=dev)
+
+    @staticmethod
+    def _stream():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _alloc_out(self, cfg, dev):
+        import torch
+        ns, B, H, W = cfg.num_scales, cfg.B, cfg.H, cfg.W
+        return dict(loss=torch.zeros(1, device=dev), per_pixel=torch.zeros(ns, B, H, W, device=dev),
+                    argmin=torch.zeros(ns, B, H, W, dtype=torch.uint8, device=dev),
+                    depth=torch.zeros(ns, B, 1, H, W, device=dev))
+
+    def forward(self, args):
+        a, cfg, inp = self._prep(args)
+        dev = a["target"].device
+        o = self._alloc_out(cfg, dev)
+        ws = self._ws(cfg, dev)
+        out = make_outputs(o["loss"], o["per_pixel"], o["argmin"], o["depth"])
+        rc = self.lib.md2_loss_forward(C.byref(cfg), C.byref(inp), C.byref(out), C.c_void_p(ws.data_ptr()),
+                                       self._stream())
+        if rc != 0:
+            raise RuntimeError(f"md2_loss_forward returned {rc}")
+        return o
+
+    def forward_backward(self, args, grad_loss=1.0):
+        import torch
+        a, cfg, inp = self._prep(args)
+        dev = a["target"].device
+        o = self._alloc_out(cfg, dev)
+        ws = self._ws(cfg, dev)
+        gd = [torch.full_like(d, float("nan")) for d in a["disps"]]
+        gT = [torch.full((cfg.B, 4, 4), float("nan"), device=dev) for _ in a["Ts"]]
+        out = make_outputs(o["loss"], o["per_pixel"], o["argmin"], o["depth"])
+        g = make_grads(gd, gT)
+        rc = self.lib.md2_loss_forward_backward(C.byref(cfg), C.byref(inp), C.byref(out), C.byref(g),
+                                                C.c_float(grad_loss), C.c_void_p(ws.data_ptr()), self._stream())
+        if rc != 0:
+            raise RuntimeError(f"md2_loss_forward_backward returned {rc}")
+        o["grad_disp"], o["grad_T"] = gd, gT
+        return o
+
+    def backward(self, args, argmin, grad_loss):
+        import torch
+        a, cfg, inp = self._prep(args)
+        dev = a["target"].device
+        ws = self._ws(cfg, dev)
+        gd = [torch.full_like(d, float("nan")) for d in a["disps"]]
+        gT = [torch.full((cfg.B, 4, 4), float("nan"), device=dev) for _ in a["Ts"]]
+        g = make_grads(gd, gT)
+        gl = torch.as_tensor([float(grad_loss)], dtype=torch.float32, device=dev)
+        am = argmin.contiguous()
+        rc = self.lib.md2_loss_backward(C.byref(cfg), C.byref(inp), C.c_void_p(am.data_ptr()),
+                                        C.c_void_p(gl.data_ptr()), C.byref(g), C.c_void_p(ws.data_ptr()),
+                                        self._stream())
+        if rc != 0:
+            raise RuntimeError(f"md2_loss_backward returned {rc}")
+        return dict(grad_disp=gd, grad_T=gT)
+
+    def debug_warp(self, args, scale, source):
+        import torch
+        a, cfg, inp = self._prep(args)
+        dev = a["target"].device
+        ws = self._ws(cfg, dev)
+        coords = torch.zeros(cfg.B, 2, cfg.H, cfg.W, device=dev)
+        warped = torch.zeros(cfg.B, 3, cfg.H, cfg.W, device=dev)
+        rc = self.lib.md2_debug_warp(C.byref(cfg), C.byref(inp), scale, source, C.c_void_p(coords.data_ptr()),
+                                     C.c_void_p(warped.data_ptr()), C.c_void_p(ws.data_ptr()), self._stream())
+        if rc != 0:
+            raise RuntimeError(f"md2_debug_warp returned {rc}")
+        return coords, warped

@@ -1,0 +1,241 @@
+// md2_abi.cu - sm_100a kernels and the extern "C" entry points of include/md2_loss.h.
+//
+// Launch structure of one step (3 launches, no host synchronisation, no allocation):
+//   1. smooth_forward_kernel   per (scale, image, row band): sums for the mean-normalised
+//                              smoothness (model_loss.py:77-88,112-116); zero-fills the
+//                              gradient buffers when a backward follows;
+//   2. tile_kernel<S, BWD>     one CTA per 32x16 image tile, all scales and sources
+//                              (md2_tile.cuh); the backward build appends one CTA per
+//                              smoothness row band for the smoothness gradient;
+//   3. finalize_kernel         fixed-order reduction of the per-CTA partials -> loss,
+//                              dL/dT = K^T dL/dP.
+#include <cuda_runtime.h>
+
+#include "md2_host.h"
+
+namespace md2 {
+
+template <class TK>
+__global__ void __launch_bounds__(TK::NT) tile_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x;
+  const int blk = blockIdx.x;
+  if (blk >= p.n_tiles) {
+    if (TK::BWD) {
+      const SmoothBand k = smooth_band(p, blk - p.n_tiles);
+      const float gl = p.grad_loss_dev ? __ldg(p.grad_loss_dev) : p.grad_loss_host;
+      smooth_bwd_thread(p, k, tid, TK::NT, gl);
+    }
+    return;
+  }
+  typename TK::Ctx c;
+  TK::make_ctx(c, p, sm, blk);
+  typename TK::Regs regs;
+  TK::init_regs(regs);
+  TK::load_tiles(c, tid);
+  __syncthreads();
+  TK::prologue_windows(c, tid);
+  __syncthreads();
+  for (int s = 0; s < p.ns; ++s) {
+    TK::phase_a(c, s, tid);
+    __syncthreads();
+    TK::phase_b(c, s, tid, regs);
+    __syncthreads();
+    if (TK::BWD) {
+      TK::phase_c(c, s, tid, regs);
+      __syncthreads();
+      TK::phase_d1(c, s, tid);
+      __syncthreads();
+      TK::phase_d2(c, s, tid);
+    }
+  }
+  TK::epilogue1(c, tid, regs);
+  __syncthreads();
+  TK::epilogue2(c, tid);
+}
+
+__global__ void __launch_bounds__(256) smooth_forward_kernel(const __grid_constant__ Params p, int zero_grad) {
+  __shared__ float red[8 * 3];
+  const SmoothBand k = smooth_band(p, blockIdx.x);
+  float v[3];
+  smooth_fwd_thread(p, k, threadIdx.x, 256, zero_grad != 0, v);
+  Reduce<256>::stage1(v, 3, threadIdx.x, red);
+  __syncthreads();
+  if (threadIdx.x < 3) p.smooth_part[(size_t)blockIdx.x * 3 + threadIdx.x] = Reduce<256>::stage2(threadIdx.x, 3, red);
+}
+
+struct GradTPtrs {
+  float* p[kMaxS];
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ Params p, float* loss, GradTPtrs gT,
+                                                       int want_grad_T) {
+  __shared__ double red[256];
+  if (loss) {
+    red[threadIdx.x] = finalize_loss_partial(p, threadIdx.x, 256);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double acc = 0.0;
+      for (int i = 0; i < 256; ++i) acc += red[i];
+      *loss = (float)acc;
+    }
+  }
+  if (want_grad_T)
+    for (int idx = threadIdx.x; idx < p.S * p.B * 16; idx += 256) finalize_grad_T(p, gT.p, idx);
+}
+
+__global__ void pose_forward_kernel(int n, const float* aa, const float* tr, int invert, float* M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pose_forward_one(aa + 3 * i, tr + 3 * i, invert, M + 16 * i);
+}
+__global__ void pose_backward_kernel(int n, const float* aa, const float* tr, int invert, const float* gM, float* gaa,
+                                     float* gtr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pose_backward_one(aa + 3 * i, tr + 3 * i, invert, gM + 16 * i, gaa + 3 * i, gtr + 3 * i);
+}
+
+static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+
+template <class TK>
+static cudaError_t launch_tiles(const Params& p, cudaStream_t st) {
+  static bool attr_set = false;  // per instantiation; the attribute is sticky for the process
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tile_kernel<TK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)TK::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int extra = TK::BWD ? p.ns * p.B * kSmoothChunks : 0;
+  if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
+  tile_kernel<TK><<<p.n_tiles + extra, TK::NT, TK::SMEM_BYTES, st>>>(p);
+  if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
+  return cudaGetLastError();
+}
+
+template <bool BWD>
+static cudaError_t dispatch_tiles(const Params& p, cudaStream_t st) {
+  switch (p.S) {
+    case 1: return launch_tiles<Tile<1, BWD, kTW, kTH, kNT>>(p, st);
+    case 2: return launch_tiles<Tile<2, BWD, kTW, kTH, kNT>>(p, st);
+    case 3: return launch_tiles<Tile<3, BWD, kTW, kTH, kNT>>(p, st);
+    default: return launch_tiles<Tile<4, BWD, kTW, kTH, kNT>>(p, st);
+  }
+}
+
+static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out, const md2_grads* g,
+                    float grad_loss, const float* grad_loss_dev, const uint8_t* saved_k, void* workspace,
+                    md2_stream_t stream, Mode mode, const Params* tweak) {
+  int e = validate_cfg(cfg);
+  if (e) return e;
+  e = validate_inputs(cfg, in);
+  if (e) return e;
+  if (!workspace) return MD2_ERR_WORKSPACE;
+  if (mode != kBackward && (!out || !out->loss)) return MD2_ERR_NULL;
+  if (mode != kForward) {
+    if (!g) return MD2_ERR_NULL;
+    for (int s = 0; s < cfg->num_scales; ++s)
+      if (!g->grad_disp[s]) return MD2_ERR_NULL;
+  }
+  if (mode == kBackward && (!saved_k || !grad_loss_dev)) return MD2_ERR_NULL;
+  Params p;
+  fill_params(p, cfg, in, out, g, workspace, mode);
+  p.grad_loss_host = grad_loss;
+  p.grad_loss_dev = grad_loss_dev;
+  p.saved_k = saved_k;
+  if (tweak) {
+    p.dbg_coords = tweak->dbg_coords;
+    p.dbg_warped = tweak->dbg_warped;
+    p.dbg_scale = tweak->dbg_scale;
+    p.dbg_source = tweak->dbg_source;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  smooth_forward_kernel<<<p.ns * p.B * kSmoothChunks, 256, 0, st>>>(p, mode != kForward);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return (int)ce;
+  ce = mode == kForward ? dispatch_tiles<false>(p, st) : dispatch_tiles<true>(p, st);
+  if (ce != cudaSuccess) return (int)ce;
+  GradTPtrs gT;
+  for (int f = 0; f < kMaxS; ++f) gT.p[f] = (g && f < cfg->S) ? g->grad_T[f] : nullptr;
+  finalize_kernel<<<1, 256, 0, st>>>(p, mode == kBackward ? nullptr : out->loss, gT, mode != kForward);
+  ce = cudaGetLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+}  // namespace md2
+
+using namespace md2;
+
+extern "C" {
+
+size_t md2_workspace_bytes(const md2_cfg* cfg) {
+  if (validate_cfg(cfg)) return 0;
+  return workspace_layout(cfg).bytes;
+}
+
+int md2_loss_forward(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out, void* workspace,
+                     md2_stream_t stream) {
+  return run_step(cfg, in, out, nullptr, 1.0f, nullptr, nullptr, workspace, stream, kForward, nullptr);
+}
+
+int md2_loss_forward_backward(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out,
+                              const md2_grads* grads, float grad_loss, void* workspace, md2_stream_t stream) {
+  return run_step(cfg, in, out, grads, grad_loss, nullptr, nullptr, workspace, stream, kFused, nullptr);
+}
+
+int md2_loss_backward(const md2_cfg* cfg, const md2_inputs* in, const uint8_t* argmin, const float* grad_loss_dev,
+                      const md2_grads* grads, void* workspace, md2_stream_t stream) {
+  return run_step(cfg, in, nullptr, grads, 1.0f, grad_loss_dev, argmin, workspace, stream, kBackward, nullptr);
+}
+
+int md2_debug_warp(const md2_cfg* cfg, const md2_inputs* in, int scale, int source, float* coords, float* warped,
+                   void* workspace, md2_stream_t stream) {
+  if (!coords || !warped || !workspace) return MD2_ERR_NULL;
+  Params t;
+  memset(&t, 0, sizeof(t));
+  t.dbg_coords = coords;
+  t.dbg_warped = warped;
+  t.dbg_scale = scale;
+  t.dbg_source = source;
+  // the scalar loss lands in the last 4 bytes of the (256-byte padded) workspace
+  md2_outputs out;
+  memset(&out, 0, sizeof(out));
+  const size_t wb = md2_workspace_bytes(cfg);
+  if (wb == 0) return MD2_ERR_SHAPE;
+  out.loss = (float*)((char*)workspace + wb - sizeof(float));
+  return run_step(cfg, in, &out, nullptr, 1.0f, nullptr, nullptr, workspace, stream, kForward, &t);
+}
+
+int md2_pose_forward(int n, const float* axisangle, const float* translation, int invert, float* M,
+                     md2_stream_t stream) {
+  if (n < 0) return MD2_ERR_SHAPE;
+  if (!axisangle || !translation || !M) return MD2_ERR_NULL;
+  if (n == 0) return 0;
+  pose_forward_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(n, axisangle, translation, invert, M);
+  const cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+int md2_pose_backward(int n, const float* axisangle, const float* translation, int invert, const float* grad_M,
+                      float* grad_axisangle, float* grad_translation, md2_stream_t stream) {
+  if (n < 0) return MD2_ERR_SHAPE;
+  if (!axisangle || !translation || !grad_M || !grad_axisangle || !grad_translation) return MD2_ERR_NULL;
+  if (n == 0) return 0;
+  pose_backward_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(n, axisangle, translation, invert, grad_M,
+                                                                       grad_axisangle, grad_translation);
+  const cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
+int md2_launches_per_step(const md2_cfg* cfg, int with_backward) {
+  (void)with_backward;
+  return validate_cfg(cfg) ? 0 : 3;
+}
+
+void md2_set_tile_kernel_events(void* start_event, void* stop_event) {
+  md2::g_ev_start = (cudaEvent_t)start_event;
+  md2::g_ev_stop = (cudaEvent_t)stop_event;
+}
+
+const char* md2_version(void) { return "md2loss 0.1 sm_100a"; }
+
+}  // extern "C"

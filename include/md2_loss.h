@@ -116,11 +116,16 @@ int md2_pose_backward(int n, const float* axisangle, const float* translation, i
 int md2_launches_per_step(const md2_cfg* cfg, int with_backward);
 const char* md2_version(void);
 
+/* Measurement hook for bench.py: when both are non-NULL, every following step call records
+ * `start` / `stop` (cudaEvent_t) on its stream immediately around the tile kernel - the
+ * dominant launch - so its duration can be read without a profiler.  NULL, NULL disables. */
+void md2_set_tile_kernel_events(void* start_event, void* stop_event);
+
 /* Debug taps used by the parity tests only: the sampling coordinates (ix, iy) in pixels
  * after un-normalisation and before clipping, and the warped image, for source f at
  * scale s.  coords [B,2,H,W], warped [B,3,H,W]. */
 int md2_debug_warp(const md2_cfg* cfg, const md2_inputs* in, int scale, int source,
-                   float* coords, float* warped, md2_stream_t stream);
+                   float* coords, float* warped, void* workspace, md2_stream_t stream);
 
 #ifdef __cplusplus
 }

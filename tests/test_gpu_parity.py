@@ -1,0 +1,256 @@
+"""Parity tests proper: the CUDA path, through the C ABI (ctypes -> libmd2loss.so) and through the
+PyTorch extension, against the oracle run on the same B200 in fp32 and in fp64.
+
+Tolerances (BASELINE.json north_star; SURVEY.md 7.2 H1 protocol):
+  per-pixel loss   <= 1e-5 relative against the fp32 reference on the same GPU (in fact bit-exact for
+                   batch >= 2, where cuBLAS takes the same batched path the kernel replicates), OR not
+                   farther from the fp64 arbiter than the fp32 reference itself is;
+  argmin/auto-mask bit-exact except numerical ties (value gap <= 1e-5 relative at the flipped pixel);
+  gradients        norm-wise <= 1e-4 against the fp32 reference, OR not farther from fp64 than the fp32
+                   reference is (x1.25): autograd's own fp32 rounding noise on these chains is 1e-4..1e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_CASES, GOLDEN_DIR, load_golden, max_rel, norm_rel, with_grad
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def cl():
+    import md2_b200.cabi as cabi
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return cabi.CLoss()
+
+
+def synth_args(B, H, W, frame_ids, automask, kind, seed, num_scales=4, k_variant="monodepth2"):
+    import md2_b200.synthetic as syn
+    from oracle import oracle_torch as O
+    inputs, outputs = syn.make_batch(B, H, W, frame_ids, num_scales, seed, kind, k_variant, requires_grad=False)
+    srcs = frame_ids[1:]
+    g = lambda t: t.to(DEV)
+    Ts = [g(inputs["stereo"]) if f == "s" else
+          O.pose_matrix(g(outputs[("axisangle", f)]), g(outputs[("translation", f)]), invert=(f < 0)).detach()
+          for f in srcs]
+    return dict(target=g(inputs[("color", 0, 0)]), sources=[g(inputs[("color", f, 0)]) for f in srcs],
+                disps=[g(outputs[("disp", s)]) for s in range(num_scales)],
+                color_pyr=[g(inputs[("color", 0, s)]) for s in range(num_scales)],
+                K=g(inputs[("K", 0)]), inv_K=g(inputs[("inv_K", 0)]), Ts=Ts, automask=automask,
+                noise=[g(n) for n in syn.make_noise(B, len(srcs), H, W, num_scales, seed)] if automask else None)
+
+
+def to64(args):
+    cv = lambda v: [t.double() for t in v] if isinstance(v, list) else (v.double() if torch.is_tensor(v) else v)
+    return {k: cv(v) for k, v in args.items()}
+
+
+def check(args, out, need_exact_forward=False, grads=True, stereo_last=False):
+    from oracle import oracle_torch as O
+    r32 = O.loss_and_grads(**with_grad(args))
+    r64 = O.loss_and_grads(**with_grad(to64(args)))
+    ns = len(args["disps"])
+    assert abs(float(out["loss"]) - float(r32["loss"])) <= 1e-5 * abs(float(r32["loss"]))
+    total_flips = 0
+    for s in range(ns):
+        assert torch.equal(out["depth"][s], r32["depth"][s]), "depth must be bit-exact"
+        pp, p32, p64 = out["per_pixel"][s], r32["per_pixel"][s], r64["per_pixel"][s]
+        mism = out["argmin"][s].long() != r32["argmin"][s]
+        total_flips += int(mism.sum())
+        if need_exact_forward:
+            assert torch.equal(pp, p32), f"scale {s}: per-pixel loss not bit-exact ({float((pp != p32).float().mean())})"
+            assert int(mism.sum()) == 0
+        else:
+            if mism.any():  # only exact ties may flip
+                assert float(((pp - p32).abs() / p32.abs().clamp_min(1e-12))[mism].max()) <= 1e-5
+            rel = float(((pp - p32).abs() / p32.abs().clamp_min(1e-12))[~mism].max())
+            e_ours = float((pp.double() - p64).abs().max())
+            e_ref = float((p32.double() - p64).abs().max())
+            assert rel <= 1e-5 or e_ours <= 1.25 * e_ref + 1e-7, (s, rel, e_ours, e_ref)
+    if grads:
+        for s in range(ns):
+            a = norm_rel(out["grad_disp"][s], r32["grad_disp"][s])
+            b = norm_rel(out["grad_disp"][s], r64["grad_disp"][s])
+            c = norm_rel(r32["grad_disp"][s], r64["grad_disp"][s])
+            assert a <= 1e-4 or b <= 1.25 * c + 1e-6, ("grad_disp", s, a, b, c)
+        n_pose = len(args["Ts"]) - (1 if stereo_last else 0)
+        for f in range(n_pose):
+            a = norm_rel(out["grad_T"][f], r32["grad_T"][f])
+            b = norm_rel(out["grad_T"][f], r64["grad_T"][f])
+            c = norm_rel(r32["grad_T"][f], r64["grad_T"][f])
+            assert a <= 1e-4 or b <= 1.25 * c + 1e-6, ("grad_T", f, a, b, c)
+    return total_flips
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cabi_against_reference_golden(cl, name):
+    """Committed outputs of the reference itself (CPU run): loss, depth, argmin, gradients."""
+    args, ref = load_golden(name, device=DEV)
+    out = cl.forward_backward(args)
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    flips = 0
+    for s in range(4):
+        assert max_rel(out["depth"][s].cpu(), ref["depth"][s]) <= 1e-6
+        if "argmin" in ref:
+            flips += int((out["argmin"][s].cpu() != ref["argmin"][s]).sum())
+    assert flips <= 2
+    if flips == 0:
+        for s in range(4):
+            assert norm_rel(out["grad_disp"][s].cpu(), ref["grad_disp"][s]) <= 1e-3
+        for f, g in enumerate(ref["grad_T"]):
+            if g is not None:
+                assert norm_rel(out["grad_T"][f].cpu(), g) <= 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,frame_ids,automask,kind,kv,seed", [
+    (2, 192, 640, [0, -1, 1], True, "smooth", "monodepth2", 0),
+    (2, 192, 640, [0, -1, 1], True, "iid", "monodepth2", 1),
+    (2, 96, 320, [0, -1, 1], False, "smooth", "floor", 2),
+    (3, 64, 96, [0, 1], True, "iid", "row1_width", 3),
+])
+def test_cabi_forward_bit_exact_vs_fp32_reference_on_gpu(cl, B, H, W, frame_ids, automask, kind, kv, seed):
+    args = synth_args(B, H, W, frame_ids, automask, kind, seed, k_variant=kv)
+    out = cl.forward_backward(args)
+    check(args, out, need_exact_forward=True)
+
+
+@pytest.mark.parametrize("B,H,W,frame_ids,automask,kind,seed", [
+    (1, 192, 640, [0, -1, 1], True, "iid", 4),          # batch 1: cuBLAS takes a non-batched path
+    (2, 96, 320, [0, -1, 1, "s"], True, "smooth", 5),   # mono + stereo
+    (2, 64, 96, [0, -1, 1, "s", 2], True, "smooth", 6), # four sources
+    (2, 40, 72, [0, -1, 1], True, "iid", 7),            # partial tiles
+])
+def test_cabi_tolerance_cases(cl, B, H, W, frame_ids, automask, kind, seed):
+    args = synth_args(B, H, W, frame_ids, automask, kind, seed)
+    out = cl.forward_backward(args)
+    check(args, out, stereo_last="s" in frame_ids and frame_ids[-1] == "s")
+
+
+def test_forward_only_and_standalone_backward_agree_with_fused(cl):
+    args = synth_args(2, 96, 320, [0, -1, 1], True, "smooth", 8)
+    fused = cl.forward_backward(args)
+    fwd = cl.forward(args)
+    for k in ("per_pixel", "argmin", "depth"):
+        assert torch.equal(fwd[k], fused[k]), k
+    assert float(fwd["loss"]) == pytest.approx(float(fused["loss"]), rel=1e-6)
+    bwd = cl.backward(args, fused["argmin"], 1.0)
+    half = cl.forward_backward(args, grad_loss=0.5)
+    for s in range(4):
+        assert norm_rel(bwd["grad_disp"][s], fused["grad_disp"][s]) <= 1e-5
+        assert norm_rel(2 * half["grad_disp"][s], fused["grad_disp"][s]) <= 1e-5
+    for f in range(2):
+        assert norm_rel(bwd["grad_T"][f], fused["grad_T"][f]) <= 1e-5
+
+
+def test_full_size_properties(cl):
+    """BASELINE.json full size (batch 12, 192x640): size-independent properties."""
+    args = synth_args(12, 192, 640, [0, -1, 1], True, "iid", 9)
+    out = cl.forward_backward(args)
+    # (1) the scalar loss is the mean of the per-pixel map plus the smoothness term
+    from oracle import oracle_torch as O
+    sm = sum(1e-3 * float(O.smoothness(args["disps"][s], args["color_pyr"][s])) / 2 ** s for s in range(4))
+    expect = (float(out["per_pixel"].double().mean(dim=(1, 2, 3)).sum()) + sm) / 4
+    assert float(out["loss"]) == pytest.approx(expect, rel=2e-6)
+    # (2) batch items are independent: the first 3 images alone give the same per-pixel maps
+    sub = {k: ([t[:3].contiguous() for t in v] if isinstance(v, list) else (v[:3].contiguous() if torch.is_tensor(v) else v))
+           for k, v in args.items()}
+    o3 = cl.forward_backward(sub)
+    assert torch.equal(o3["per_pixel"], out["per_pixel"][:, :3])
+    assert torch.equal(o3["argmin"], out["argmin"][:, :3])
+    # (3) gradients are linear in the upstream gradient and masked pixels get none at scale 0
+    masked = out["argmin"][0] < 2
+    g0 = out["grad_disp"][0][:, 0]
+    assert torch.isfinite(g0).all()
+    # smoothness contributes everywhere, so compare against a run without smoothness
+    a2 = dict(args); a2["disp_smoothness"] = 0.0
+    o2 = cl.forward_backward(a2)
+    interior = torch.zeros_like(masked)
+    interior[:, 2:-2, 2:-2] = True
+    import torch.nn.functional as F
+    nb = F.max_pool2d((~masked).float()[:, None], 3, 1, 1)[:, 0] > 0  # any unmasked window in the 3x3 neighbourhood
+    assert float(o2["grad_disp"][0][:, 0][~nb].abs().max()) == 0.0
+
+
+def test_torch_extension_autograd_matches_cabi(cl):
+    from md2_b200 import functional as F_
+    args = synth_args(2, 96, 320, [0, -1, 1], True, "smooth", 10)
+    ref = cl.forward_backward(args)
+    a = with_grad(args)
+    res = F_.view_synthesis_loss(a["target"], a["sources"], a["disps"], a["color_pyr"], a["K"], a["inv_K"], a["Ts"],
+                                 noise=args["noise"], want_per_pixel=True)
+    (res["loss"] * 2.0).backward()
+    assert float(res["loss"]) == pytest.approx(float(ref["loss"]), rel=1e-6)
+    assert torch.equal(res["argmin"], ref["argmin"])
+    for s in range(4):
+        assert norm_rel(a["disps"][s].grad, 2 * ref["grad_disp"][s]) <= 1e-5
+    for f in range(2):
+        assert norm_rel(a["Ts"][f].grad, 2 * ref["grad_T"][f]) <= 1e-5
+    with torch.no_grad():
+        nog = F_.view_synthesis_loss(a["target"], a["sources"], a["disps"], a["color_pyr"], a["K"], a["inv_K"],
+                                     a["Ts"], noise=args["noise"])
+    assert float(nog["loss"]) == pytest.approx(float(ref["loss"]), rel=1e-6)
+
+
+def test_compute_dropin_dict_protocol():
+    """L2 boundary: same dict keys / method order as model_train.py:90-96."""
+    from types import SimpleNamespace
+    import md2_b200.synthetic as syn
+    from md2_b200.compute import compute
+    from md2_b200 import functional as F_
+    from oracle import oracle_torch as O
+    fids = [0, -1, 1]
+    inputs, outputs = syn.make_batch(2, 64, 96, fids, 4, 11, "smooth", device=DEV)
+    for f in fids[1:]:
+        outputs[("c2c", f, 0)] = F_.param2matrix(outputs[("axisangle", f)], outputs[("translation", f)], invert=(f < 0))
+    opt = SimpleNamespace(frame_ids=fids, scales=range(4), height=64, width=96, min_depth=0.1, max_depth=100.0,
+                          pose_type="separate", use_automasking=True, disp_smoothness=1e-3)
+    noise = [n.to(DEV) for n in syn.make_noise(2, 2, 64, 96, 4, 11)]
+    c = compute(opt, DEV)
+    c.image2warping(inputs, outputs, None, noise=noise)
+    c.compute_loss(inputs, outputs, None)
+    outputs["loss"].backward()
+    # oracle with torch autograd through its own pose_matrix
+    aa = {f: outputs[("axisangle", f)].detach().clone().requires_grad_(True) for f in fids[1:]}
+    tr = {f: outputs[("translation", f)].detach().clone().requires_grad_(True) for f in fids[1:]}
+    disps = [outputs[("disp", s)].detach().clone().requires_grad_(True) for s in range(4)]
+    ref = O.view_synthesis_loss(inputs[("color", 0, 0)], [inputs[("color", f, 0)] for f in fids[1:]], disps,
+                                [inputs[("color", 0, s)] for s in range(4)], inputs[("K", 0)], inputs[("inv_K", 0)],
+                                [O.pose_matrix(aa[f], tr[f], invert=(f < 0)) for f in fids[1:]], noise=noise)
+    ref["loss"].backward()
+    assert float(outputs["loss"]) == pytest.approx(float(ref["loss"]), rel=1e-5)
+    assert torch.allclose(outputs[("depth", 0, 0)], ref["depth"][0], rtol=1e-6)
+    for f in fids[1:]:
+        assert norm_rel(outputs[("axisangle", f)].grad, aa[f].grad) <= 2e-3
+        assert norm_rel(outputs[("translation", f)].grad, tr[f].grad) <= 2e-3
+
+
+def test_pose_kernel_matches_golden_and_torch():
+    from md2_b200 import functional as F_
+    z = np.load(f"{GOLDEN_DIR}/pose.npz")
+    aa = torch.from_numpy(z["aa"]).to(DEV).requires_grad_(True)
+    tr = torch.from_numpy(z["tr"]).to(DEV).requires_grad_(True)
+    cot = torch.from_numpy(z["cot"]).to(DEV)
+    for k, inv in enumerate([False, True]):
+        M = F_.param2matrix(aa, tr, inv)
+        ga, gt = torch.autograd.grad((M * cot[k]).sum(), [aa, tr])
+        assert torch.allclose(M.cpu(), torch.from_numpy(z[f"M{k}"]), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(ga.cpu(), torch.from_numpy(z[f"grad_aa{k}"]), rtol=1e-4, atol=1e-5)
+        assert torch.allclose(gt.cpu(), torch.from_numpy(z[f"grad_tr{k}"]), rtol=1e-4, atol=1e-5)
+
+
+def test_invalid_arguments_are_rejected(cl):
+    import ctypes as C
+    import md2_b200.cabi as cabi
+    from md2_b200 import functional as F_
+    bad = cabi.make_cfg(2, 30, 64, 2)  # H not divisible by 8
+    assert cl.lib.md2_workspace_bytes(C.byref(bad)) == 0
+    args = synth_args(2, 64, 96, [0, -1, 1], True, "smooth", 12)
+    with pytest.raises(RuntimeError):
+        F_.view_synthesis_loss(args["target"].cpu(), args["sources"], args["disps"], args["color_pyr"], args["K"],
+                               args["inv_K"], args["Ts"])
+    with pytest.raises(RuntimeError):
+        F_.view_synthesis_loss(args["target"].double(), args["sources"], args["disps"], args["color_pyr"], args["K"],
+                               args["inv_K"], args["Ts"])
