@@ -59,23 +59,53 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~2 ms period;
+    nvidia-smi as a fallback)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.mx, self.reasons, self.stop_flag = index, [], 0, set(), False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                          ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=5)
+        r = [x.strip() for x in o.stdout.strip().split(",")]
+        self.sm.append(float(r[0]))
+        self.mx = max(self.mx, float(r[1]))
+        for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(n)
 
     def _run(self):
         while not self.stop_flag:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([x.strip() for x in o.stdout.strip().split(",")])
+                if self.nv:
+                    self._sample_nvml()
+                    time.sleep(0.002)
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            time.sleep(0.1)
+                time.sleep(0.05)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -87,22 +117,9 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 6:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def make_host_batch(seed):
@@ -297,7 +314,7 @@ def cpu_step_fn():
         T = [t.clone().requires_grad_(True) for t in Ts]
         out = O.view_synthesis_loss(disps=disps, Ts=T, **base)
         out["loss"].backward()
-        return float(out["loss"])
+        return float(out["loss"].detach())
     return step
 
 
