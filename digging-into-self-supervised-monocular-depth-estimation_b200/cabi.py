@@ -48,7 +48,8 @@ class md2_grads(C.Structure):
 # every symbol include/md2_loss.h declares
 EXPORTS = ["md2_workspace_bytes", "md2_loss_forward", "md2_loss_forward_backward",
            "md2_loss_backward", "md2_pose_forward", "md2_pose_backward",
-           "md2_launches_per_step", "md2_version", "md2_debug_warp", "md2_set_tile_kernel_events"]
+           "md2_launches_per_step", "md2_version", "md2_debug_warp", "md2_set_tile_kernel_events",
+           "md2_debug_div"]
 
 LIB_NAME = "libmd2loss.so"
 
@@ -88,6 +89,8 @@ def load_library(path=None):
     lib.md2_version.argtypes = []
     lib.md2_set_tile_kernel_events.restype = None
     lib.md2_set_tile_kernel_events.argtypes = [C.c_void_p, C.c_void_p]
+    lib.md2_debug_div.restype = C.c_int
+    lib.md2_debug_div.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.md2_debug_warp.restype = C.c_int
     lib.md2_debug_warp.argtypes = [C.POINTER(md2_cfg), C.POINTER(md2_inputs), C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

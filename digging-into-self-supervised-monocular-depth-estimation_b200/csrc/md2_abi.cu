@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(TK::NT) tile_kernel(const __grid_constant__ Pa
   TK::make_ctx(c, p, sm, blk);
   typename TK::Regs regs;
   TK::init_regs(regs);
+  TK::setup(c, tid);
   TK::load_tiles(c, tid);
   __syncthreads();
   TK::prologue_windows(c, tid);
@@ -68,20 +69,48 @@ struct GradTPtrs {
   float* p[kMaxS];
 };
 
+// block 0: the scalar loss; blocks 1 + (f * B + b): dL/dT_f[b] = K_b^T (sum over the image's tiles of dL/dP)
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ Params p, float* loss, GradTPtrs gT,
                                                        int want_grad_T) {
   __shared__ double red[256];
-  if (loss) {
-    red[threadIdx.x] = finalize_loss_partial(p, threadIdx.x, 256);
+  __shared__ float part[21 * 12];
+  __shared__ float dPs[12];
+  const int t = threadIdx.x;
+  if (blockIdx.x == 0) {
+    if (!loss) return;
+    red[t] = finalize_loss_partial(p, t, 256);
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double acc = 0.0;
-      for (int i = 0; i < 256; ++i) acc += red[i];
-      *loss = (float)acc;
+    for (int o = 128; o > 0; o >>= 1) {  // fixed-shape tree: deterministic
+      if (t < o) red[t] += red[t + o];
+      __syncthreads();
     }
+    if (t == 0) *loss = (float)red[0];
+    return;
   }
-  if (want_grad_T)
-    for (int idx = threadIdx.x; idx < p.S * p.B * 16; idx += 256) finalize_grad_T(p, gT.p, idx);
+  if (!want_grad_T) return;
+  const int fb = blockIdx.x - 1;
+  const int b = fb % p.B, f = fb / p.B;
+  if (f >= p.S || gT.p[f] == nullptr) return;
+  const int per_img = p.tiles_x * p.tiles_y;
+  if (t < 21 * 12) {
+    const int v = t % 12, g = t / 12;
+    float acc = 0.f;
+    for (int tile = g; tile < per_img; tile += 21)
+      acc += p.dP_part[((size_t)(b * per_img + tile) * p.S + f) * 12 + v];
+    part[g * 12 + v] = acc;
+  }
+  __syncthreads();
+  if (t < 12) {
+    float acc = 0.f;
+    for (int g = 0; g < 21; ++g) acc += part[g * 12 + t];
+    dPs[t] = acc;
+  }
+  __syncthreads();
+  if (t < 16) {
+    const int k = t >> 2, j = t & 3;
+    const float* K = p.K + b * 16;
+    gT.p[f][b * 16 + t] = K[0 * 4 + k] * dPs[0 * 4 + j] + K[1 * 4 + k] * dPs[1 * 4 + j] + K[2 * 4 + k] * dPs[2 * 4 + j];
+  }
 }
 
 __global__ void pose_forward_kernel(int n, const float* aa, const float* tr, int invert, float* M) {
@@ -92,6 +121,14 @@ __global__ void pose_backward_kernel(int n, const float* aa, const float* tr, in
                                      float* gtr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) pose_backward_one(aa + 3 * i, tr + 3 * i, invert, gM + 16 * i, gaa + 3 * i, gtr + 3 * i);
+}
+
+__global__ void debug_div_kernel(int n, const float* num, const float* den, float* q_div, float* q9) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    q_div[i] = div_pos(num[i], den[i]);
+    q9[i] = div9(num[i]);
+  }
 }
 
 static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
@@ -105,7 +142,7 @@ static cudaError_t launch_tiles(const Params& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int extra = TK::BWD ? p.ns * p.B * kSmoothChunks : 0;
+  const int extra = TK::BWD ? p.B * smooth_total(p.ns) : 0;
   if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
   tile_kernel<TK><<<p.n_tiles + extra, TK::NT, TK::SMEM_BYTES, st>>>(p);
   if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
@@ -149,14 +186,15 @@ static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs*
     p.dbg_source = tweak->dbg_source;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  smooth_forward_kernel<<<p.ns * p.B * kSmoothChunks, 256, 0, st>>>(p, mode != kForward);
+  smooth_forward_kernel<<<p.B * smooth_total(p.ns), 256, 0, st>>>(p, mode != kForward);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return (int)ce;
   ce = mode == kForward ? dispatch_tiles<false>(p, st) : dispatch_tiles<true>(p, st);
   if (ce != cudaSuccess) return (int)ce;
   GradTPtrs gT;
   for (int f = 0; f < kMaxS; ++f) gT.p[f] = (g && f < cfg->S) ? g->grad_T[f] : nullptr;
-  finalize_kernel<<<1, 256, 0, st>>>(p, mode == kBackward ? nullptr : out->loss, gT, mode != kForward);
+  finalize_kernel<<<1 + (mode != kForward ? p.B * p.S : 0), 256, 0, st>>>(p, mode == kBackward ? nullptr : out->loss, gT,
+                                                                            mode != kForward);
   ce = cudaGetLastError();
   return ce == cudaSuccess ? 0 : (int)ce;
 }
@@ -229,6 +267,14 @@ int md2_pose_backward(int n, const float* axisangle, const float* translation, i
 int md2_launches_per_step(const md2_cfg* cfg, int with_backward) {
   (void)with_backward;
   return validate_cfg(cfg) ? 0 : 3;
+}
+
+int md2_debug_div(int n, const float* num, const float* den, float* q_div, float* q9, md2_stream_t stream) {
+  if (n <= 0) return MD2_ERR_SHAPE;
+  if (!num || !den || !q_div || !q9) return MD2_ERR_NULL;
+  md2::debug_div_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, num, den, q_div, q9);
+  const cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
 }
 
 void md2_set_tile_kernel_events(void* start_event, void* stop_event) {

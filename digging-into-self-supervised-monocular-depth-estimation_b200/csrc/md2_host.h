@@ -58,7 +58,7 @@ inline Workspace workspace_layout(const md2_cfg* c) {
   w.off_dP = o;
   o += (size_t)w.n_tiles * c->S * 12 * sizeof(float);
   w.off_smooth = o;
-  o += (size_t)c->num_scales * c->B * kSmoothChunks * 3 * sizeof(float);
+  o += (size_t)c->B * smooth_total(c->num_scales) * 3 * sizeof(float);
   w.bytes = (o + 255) & ~(size_t)255;
   return w;
 }

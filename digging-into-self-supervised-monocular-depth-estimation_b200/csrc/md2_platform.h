@@ -13,9 +13,11 @@
 #if defined(__CUDACC__)
 #define MD2_DEVICE_BUILD 1
 #define MD2_FN __device__ __forceinline__
+#define MD2_HD __host__ __device__ __forceinline__
 #else
 #define MD2_DEVICE_BUILD 0
 #define MD2_FN inline
+#define MD2_HD inline
 #endif
 
 namespace md2 {
@@ -46,8 +48,8 @@ MD2_FN uint8_t ld_ro(const uint8_t* p) { return *p; }
 MD2_FN void atomic_add(float* p, float v) { *p += v; }
 #endif
 
-MD2_FN int imin(int a, int b) { return a < b ? a : b; }
-MD2_FN int imax(int a, int b) { return a > b ? a : b; }
+MD2_HD int imin(int a, int b) { return a < b ? a : b; }
+MD2_HD int imax(int a, int b) { return a > b ? a : b; }
 
 // ---- counter-based N(0,1) for the auto-mask tie-breaker when no noise is supplied ----
 MD2_FN uint64_t splitmix64(uint64_t x) {

@@ -127,6 +127,10 @@ void md2_set_tile_kernel_events(void* start_event, void* stop_event);
 int md2_debug_warp(const md2_cfg* cfg, const md2_inputs* in, int scale, int source,
                    float* coords, float* warped, void* workspace, md2_stream_t stream);
 
+/* Test hook: q_div[i] = num[i] / den[i] and q9[i] = num[i] / 9 computed with the kernels' guard-free
+ * division sequences (csrc/md2_tile.cuh div_pos / div9), to be compared with IEEE division. */
+int md2_debug_div(int n, const float* num, const float* den, float* q_div, float* q9, md2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,7 @@ static void run_tiles(const Params& p) {
     typename TK::Ctx c;
     TK::make_ctx(c, p, sm.data(), tile);
     PHASE(TK::init_regs(regs[tid]));
+    PHASE(TK::setup(c, tid));
     PHASE(TK::load_tiles(c, tid));
     PHASE(TK::prologue_windows(c, tid));
     for (int s = 0; s < p.ns; ++s) {
@@ -51,7 +52,7 @@ static void dispatch_tiles(const Params& p) {
 static void run_smooth_forward(const Params& p, bool zero_grad) {
   const int nt = 256;
   std::vector<float> red(nt * 3);
-  for (int blk = 0; blk < p.ns * p.B * kSmoothChunks; ++blk) {
+  for (int blk = 0; blk < p.B * smooth_total(p.ns); ++blk) {
     const SmoothBand k = smooth_band(p, blk);
     for (int tid = 0; tid < nt; ++tid) {
       float v[3];
@@ -65,7 +66,7 @@ static void run_smooth_forward(const Params& p, bool zero_grad) {
 static void run_smooth_backward(const Params& p) {
   const int nt = 256;
   const float gl = p.grad_loss_dev ? *p.grad_loss_dev : p.grad_loss_host;
-  for (int blk = 0; blk < p.ns * p.B * kSmoothChunks; ++blk) {
+  for (int blk = 0; blk < p.B * smooth_total(p.ns); ++blk) {
     const SmoothBand k = smooth_band(p, blk);
     for (int tid = 0; tid < nt; ++tid) smooth_bwd_thread(p, k, tid, nt, gl);
   }
