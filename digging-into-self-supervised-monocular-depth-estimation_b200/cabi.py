@@ -55,7 +55,8 @@ LIB_NAME = "libmd2loss.so"
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    # MD2_LIB selects an alternative build of the same library (tile-shape experiments, tools/variants.py)
+    return os.environ.get("MD2_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 def load_library(path=None):

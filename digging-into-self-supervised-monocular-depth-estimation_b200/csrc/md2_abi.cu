@@ -15,21 +15,25 @@
 
 namespace md2 {
 
-template <class TK>
-__global__ void __launch_bounds__(TK::NT) tile_kernel(const __grid_constant__ Params p) {
+// grid (tiles_x, tiles_y, B + extra): z < B are image tiles; the extra z-layers of the backward build
+// enumerate the smoothness row bands
+template <class TK, bool DBG>
+__global__ void __launch_bounds__(TK::NT, TK::BWD ? MD2_MINB : 1) tile_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
-  const int blk = blockIdx.x;
-  if (blk >= p.n_tiles) {
+  if ((int)blockIdx.z >= p.B) {
     if (TK::BWD) {
-      const SmoothBand k = smooth_band(p, blk - p.n_tiles);
-      const float gl = p.grad_loss_dev ? __ldg(p.grad_loss_dev) : p.grad_loss_host;
-      smooth_bwd_thread(p, k, tid, TK::NT, gl);
+      const int blk = ((blockIdx.z - p.B) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      if (blk < p.B * smooth_total(p.ns)) {
+        const SmoothBand k = smooth_band(p, blk);
+        const float gl = p.grad_loss_dev ? __ldg(p.grad_loss_dev) : p.grad_loss_host;
+        smooth_bwd_thread(p, k, tid, TK::NT, gl);
+      }
     }
     return;
   }
   typename TK::Ctx c;
-  TK::make_ctx(c, p, sm, blk);
+  TK::make_ctx(c, p, sm, blockIdx.x, blockIdx.y, blockIdx.z);
   typename TK::Regs regs;
   TK::init_regs(regs);
   TK::setup(c, tid);
@@ -38,7 +42,7 @@ __global__ void __launch_bounds__(TK::NT) tile_kernel(const __grid_constant__ Pa
   TK::prologue_windows(c, tid);
   __syncthreads();
   for (int s = 0; s < p.ns; ++s) {
-    TK::phase_a(c, s, tid);
+    TK::template phase_a<DBG>(c, s, tid);
     __syncthreads();
     TK::phase_b(c, s, tid, regs);
     __syncthreads();
@@ -126,37 +130,51 @@ __global__ void pose_backward_kernel(int n, const float* aa, const float* tr, in
 __global__ void debug_div_kernel(int n, const float* num, const float* den, float* q_div, float* q9) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    q_div[i] = div_pos(num[i], den[i]);
+    float rinv;
+    q_div[i] = div_pos(num[i], den[i], rinv);
     q9[i] = div9(num[i]);
   }
 }
 
 static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 
-template <class TK>
-static cudaError_t launch_tiles(const Params& p, cudaStream_t st) {
+template <class TK, bool DBG>
+static cudaError_t launch_tiles_impl(const Params& p, cudaStream_t st) {
   static bool attr_set = false;  // per instantiation; the attribute is sticky for the process
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tile_kernel<TK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tile_kernel<TK, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)TK::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int extra = TK::BWD ? p.B * smooth_total(p.ns) : 0;
+  const int per_layer = p.tiles_x * p.tiles_y;
+  const int extra = TK::BWD ? (p.B * smooth_total(p.ns) + per_layer - 1) / per_layer : 0;
+  const dim3 grid(p.tiles_x, p.tiles_y, p.B + extra);
   if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
-  tile_kernel<TK><<<p.n_tiles + extra, TK::NT, TK::SMEM_BYTES, st>>>(p);
+  tile_kernel<TK, DBG><<<grid, TK::NT, TK::SMEM_BYTES, st>>>(p);
   if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
   return cudaGetLastError();
 }
 
+template <class TK>
+static cudaError_t launch_tiles(const Params& p, cudaStream_t st) {
+  if (!TK::BWD && p.dbg_coords) return launch_tiles_impl<TK, !TK::BWD>(p, st);  // debug tap: forward build only
+  return launch_tiles_impl<TK, false>(p, st);
+}
+
+template <bool BWD, bool MMFMA>
+static cudaError_t dispatch_tiles_s(const Params& p, cudaStream_t st) {
+  switch (p.S) {
+    case 1: return launch_tiles<Tile<1, BWD, kTW, kTH, kNT, MMFMA>>(p, st);
+    case 2: return launch_tiles<Tile<2, BWD, kTW, kTH, kNT, MMFMA>>(p, st);
+    case 3: return launch_tiles<Tile<3, BWD, kTW, kTH, kNT, MMFMA>>(p, st);
+    default: return launch_tiles<Tile<4, BWD, kTW, kTH, kNT, MMFMA>>(p, st);
+  }
+}
 template <bool BWD>
 static cudaError_t dispatch_tiles(const Params& p, cudaStream_t st) {
-  switch (p.S) {
-    case 1: return launch_tiles<Tile<1, BWD, kTW, kTH, kNT>>(p, st);
-    case 2: return launch_tiles<Tile<2, BWD, kTW, kTH, kNT>>(p, st);
-    case 3: return launch_tiles<Tile<3, BWD, kTW, kTH, kNT>>(p, st);
-    default: return launch_tiles<Tile<4, BWD, kTW, kTH, kNT>>(p, st);
-  }
+  // batch 1: torch.matmul rounds the products of its 3- / 4-term dot products separately (see Tile)
+  return p.B > 1 ? dispatch_tiles_s<BWD, true>(p, st) : dispatch_tiles_s<BWD, false>(p, st);
 }
 
 static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out, const md2_grads* g,

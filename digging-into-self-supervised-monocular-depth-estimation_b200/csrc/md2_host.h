@@ -13,9 +13,21 @@
 namespace md2 {
 
 // tile shapes of the two kernel families (see DESIGN.md "Data layout")
-constexpr int kTW = 32;
-constexpr int kTH = 16;
-constexpr int kNT = 256;
+#ifndef MD2_TW
+#define MD2_TW 32
+#endif
+#ifndef MD2_TH
+#define MD2_TH 16
+#endif
+#ifndef MD2_NT
+#define MD2_NT 256
+#endif
+#ifndef MD2_MINB
+#define MD2_MINB 2
+#endif
+constexpr int kTW = MD2_TW;
+constexpr int kTH = MD2_TH;
+constexpr int kNT = MD2_NT;
 
 enum Mode { kForward = 0, kFused = 1, kBackward = 2 };
 

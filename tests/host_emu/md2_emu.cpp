@@ -20,13 +20,14 @@ static void run_tiles(const Params& p) {
   std::vector<typename TK::Regs> regs(TK::NT);
   for (int tile = 0; tile < p.n_tiles; ++tile) {
     typename TK::Ctx c;
-    TK::make_ctx(c, p, sm.data(), tile);
+    const int per_img = p.tiles_x * p.tiles_y, t = tile % per_img;
+    TK::make_ctx(c, p, sm.data(), t % p.tiles_x, t / p.tiles_x, tile / per_img);
     PHASE(TK::init_regs(regs[tid]));
     PHASE(TK::setup(c, tid));
     PHASE(TK::load_tiles(c, tid));
     PHASE(TK::prologue_windows(c, tid));
     for (int s = 0; s < p.ns; ++s) {
-      PHASE(TK::phase_a(c, s, tid));
+      PHASE(TK::template phase_a<true>(c, s, tid));
       PHASE(TK::phase_b(c, s, tid, regs[tid]));
       if (TK::BWD) {
         PHASE(TK::phase_c(c, s, tid, regs[tid]));
@@ -39,14 +40,18 @@ static void run_tiles(const Params& p) {
   }
 }
 
+template <bool BWD, bool MMFMA>
+static void dispatch_tiles_s(const Params& p) {
+  switch (p.S) {
+    case 1: run_tiles<Tile<1, BWD, kTW, kTH, kNT, MMFMA>>(p); break;
+    case 2: run_tiles<Tile<2, BWD, kTW, kTH, kNT, MMFMA>>(p); break;
+    case 3: run_tiles<Tile<3, BWD, kTW, kTH, kNT, MMFMA>>(p); break;
+    default: run_tiles<Tile<4, BWD, kTW, kTH, kNT, MMFMA>>(p); break;
+  }
+}
 template <bool BWD>
 static void dispatch_tiles(const Params& p) {
-  switch (p.S) {
-    case 1: run_tiles<Tile<1, BWD, kTW, kTH, kNT>>(p); break;
-    case 2: run_tiles<Tile<2, BWD, kTW, kTH, kNT>>(p); break;
-    case 3: run_tiles<Tile<3, BWD, kTW, kTH, kNT>>(p); break;
-    default: run_tiles<Tile<4, BWD, kTW, kTH, kNT>>(p); break;
-  }
+  if (p.B > 1) dispatch_tiles_s<BWD, true>(p); else dispatch_tiles_s<BWD, false>(p);
 }
 
 static void run_smooth_forward(const Params& p, bool zero_grad) {
