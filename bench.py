@@ -357,15 +357,66 @@ def run_reference(args):
     }), flush=True)
 
 
+def run_train_step(args):
+    """BASELINE.json configs[2]: full mono training step, ResNet-18 depth + separate pose network (stock
+    PyTorch/cuDNN), batch 12 per GPU, DDP.  --loss fused | eager (eager = PyTorch-op restatement of the
+    reference loss, i.e. the reference's own training step on the same GPU)."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import train_step as ts
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    step, imgs = ts.make_step(args.loss, B, H, W, FRAME_IDS, dev, ddp=world > 1)
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"metric": "train_images_per_sec", "value": imgs * world * args.steps / (ms * 1e-3),
+                          "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "dtype": "f32", "data": "synthetic", "loss_impl": args.loss, "final_loss": float(loss.detach()),
+                          "config": {"workload": "mono training step: ResNet-18 depth + separate ResNet-18 pose net, "
+                                                 "batch 12 per GPU, 192x640, frame_ids [0,-1,1], 4 scales, Adam, fp32",
+                                     "parallelism": f"ddp{world}"},
+                          "clocks": clk.summary()}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="loss", choices=["loss", "train_step"])
+    ap.add_argument("--loss", default="fused", choices=["fused", "eager"])
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
-    if a.impl == "reference":
+    if a.workload == "train_step":
+        run_train_step(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

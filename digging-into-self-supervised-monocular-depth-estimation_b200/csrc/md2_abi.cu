@@ -162,19 +162,22 @@ static cudaError_t launch_tiles(const Params& p, cudaStream_t st) {
   return launch_tiles_impl<TK, false>(p, st);
 }
 
-template <bool BWD, bool MMFMA>
+template <bool BWD, int MM>
 static cudaError_t dispatch_tiles_s(const Params& p, cudaStream_t st) {
   switch (p.S) {
-    case 1: return launch_tiles<Tile<1, BWD, kTW, kTH, kNT, MMFMA>>(p, st);
-    case 2: return launch_tiles<Tile<2, BWD, kTW, kTH, kNT, MMFMA>>(p, st);
-    case 3: return launch_tiles<Tile<3, BWD, kTW, kTH, kNT, MMFMA>>(p, st);
-    default: return launch_tiles<Tile<4, BWD, kTW, kTH, kNT, MMFMA>>(p, st);
+    case 1: return launch_tiles<Tile<1, BWD, kTW, tile_h(1), kNT, MM>>(p, st);
+    case 2: return launch_tiles<Tile<2, BWD, kTW, tile_h(2), kNT, MM>>(p, st);
+    case 3: return launch_tiles<Tile<3, BWD, kTW, tile_h(3), kNT, MM>>(p, st);
+    default: return launch_tiles<Tile<4, BWD, kTW, tile_h(4), kNT, MM>>(p, st);
   }
 }
 template <bool BWD>
 static cudaError_t dispatch_tiles(const Params& p, cudaStream_t st) {
-  // batch 1: torch.matmul rounds the products of its 3- / 4-term dot products separately (see Tile)
-  return p.B > 1 ? dispatch_tiles_s<BWD, true>(p, st) : dispatch_tiles_s<BWD, false>(p, st);
+  switch (matmul_mode(p.B, p.H, p.W)) {
+    case 0: return dispatch_tiles_s<BWD, 0>(p, st);
+    case 1: return dispatch_tiles_s<BWD, 1>(p, st);
+    default: return dispatch_tiles_s<BWD, 2>(p, st);
+  }
 }
 
 static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out, const md2_grads* g,

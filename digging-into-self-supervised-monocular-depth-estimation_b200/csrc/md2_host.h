@@ -28,8 +28,19 @@ namespace md2 {
 constexpr int kTW = MD2_TW;
 constexpr int kTH = MD2_TH;
 constexpr int kNT = MD2_NT;
+// Tile height per source count: the backward build keeps S-proportional buffers in shared memory, so the
+// tile shrinks with S to keep two CTAs resident per SM (<= ~113 KB each).
+constexpr int tile_h(int S) { return S <= 2 ? kTH : (S == 3 ? (kTH * 3) / 4 : kTH / 2); }
 
 enum Mode { kForward = 0, kFused = 1, kBackward = 2 };
+
+// Which rounding torch.matmul applies to the per-pixel dot products (see Tile's MM_ parameter)
+inline int matmul_mode(int B, int H, int W) {
+  if (B > 1) return 0;
+  const long long n = (long long)H * W;
+  if (3 * n >= 786432) return 0;
+  return 4 * n >= 786432 ? 2 : 1;
+}
 
 inline int validate_cfg(const md2_cfg* c) {
   if (!c) return MD2_ERR_NULL;
@@ -62,7 +73,7 @@ struct Workspace {
 inline Workspace workspace_layout(const md2_cfg* c) {
   Workspace w;
   w.tiles_x = (c->W + kTW - 1) / kTW;
-  w.tiles_y = (c->H + kTH - 1) / kTH;
+  w.tiles_y = (c->H + tile_h(c->S) - 1) / tile_h(c->S);
   w.n_tiles = w.tiles_x * w.tiles_y * c->B;
   size_t o = 0;
   w.off_tile_loss = o;
@@ -81,6 +92,7 @@ inline void fill_params(Params& p, const md2_cfg* c, const md2_inputs* in, const
   p.B = c->B; p.H = c->H; p.W = c->W; p.S = c->S; p.ns = c->num_scales;
   p.automask = c->automask ? 1 : 0;
   p.use_saved_k = mode == kBackward;
+  p.kt_fma = c->B > 1;
   // disparity2depth evaluates its scalars in Python doubles (warp.py:34-37)
   const double min_disp = 1.0 / c->max_depth, max_disp = 1.0 / c->min_depth;
   p.a = (float)min_disp;

@@ -40,18 +40,22 @@ static void run_tiles(const Params& p) {
   }
 }
 
-template <bool BWD, bool MMFMA>
+template <bool BWD, int MM>
 static void dispatch_tiles_s(const Params& p) {
   switch (p.S) {
-    case 1: run_tiles<Tile<1, BWD, kTW, kTH, kNT, MMFMA>>(p); break;
-    case 2: run_tiles<Tile<2, BWD, kTW, kTH, kNT, MMFMA>>(p); break;
-    case 3: run_tiles<Tile<3, BWD, kTW, kTH, kNT, MMFMA>>(p); break;
-    default: run_tiles<Tile<4, BWD, kTW, kTH, kNT, MMFMA>>(p); break;
+    case 1: run_tiles<Tile<1, BWD, kTW, tile_h(1), kNT, MM>>(p); break;
+    case 2: run_tiles<Tile<2, BWD, kTW, tile_h(2), kNT, MM>>(p); break;
+    case 3: run_tiles<Tile<3, BWD, kTW, tile_h(3), kNT, MM>>(p); break;
+    default: run_tiles<Tile<4, BWD, kTW, tile_h(4), kNT, MM>>(p); break;
   }
 }
 template <bool BWD>
 static void dispatch_tiles(const Params& p) {
-  if (p.B > 1) dispatch_tiles_s<BWD, true>(p); else dispatch_tiles_s<BWD, false>(p);
+  switch (matmul_mode(p.B, p.H, p.W)) {
+    case 0: dispatch_tiles_s<BWD, 0>(p); break;
+    case 1: dispatch_tiles_s<BWD, 1>(p); break;
+    default: dispatch_tiles_s<BWD, 2>(p); break;
+  }
 }
 
 static void run_smooth_forward(const Params& p, bool zero_grad) {

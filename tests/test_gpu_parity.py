@@ -114,6 +114,8 @@ def test_cabi_against_reference_golden(cl, name):
     # products separately; the kernels switch to the same sequence (Tile<..., MMFMA=false>)
     (1, 192, 640, [0, -1, 1], True, "iid", "monodepth2", 13),
     (1, 64, 96, [0, -1, 1], True, "smooth", "floor", 14),
+    # ... unless the right-hand matrix has >= 786432 elements, where it is an FMA chain again
+    (1, 320, 1024, [0, -1, 1], False, "smooth", "monodepth2", 15),   # 3*H*W and 4*H*W above the threshold
 ])
 def test_cabi_forward_bit_exact_vs_fp32_reference_on_gpu(cl, B, H, W, frame_ids, automask, kind, kv, seed):
     args = synth_args(B, H, W, frame_ids, automask, kind, seed, k_variant=kv)
@@ -123,7 +125,7 @@ def test_cabi_forward_bit_exact_vs_fp32_reference_on_gpu(cl, B, H, W, frame_ids,
 
 @pytest.mark.parametrize("B,H,W,frame_ids,automask,kind,seed", [
     (1, 192, 640, [0, -1, 1], True, "iid", 4),
-    (1, 320, 1024, [0, -1, 1], False, "smooth", 15),    # batch 1, high resolution: cuBLAS heuristics pick yet another kernel
+    (1, 384, 640, [0, 1], True, "iid", 16),             # batch 1 between the two cuBLAS kernel-selection thresholds
     (2, 96, 320, [0, -1, 1, "s"], True, "smooth", 5),   # mono + stereo
     (2, 64, 96, [0, -1, 1, "s", 2], True, "smooth", 6), # four sources
     (2, 40, 72, [0, -1, 1], True, "iid", 7),            # partial tiles

@@ -29,7 +29,7 @@ def cands(A, X):
     out["exact"] = f32((A.double() @ X.double()))
     return out
 g = torch.Generator(device=dev).manual_seed(0)
-H, W = 192, 640
+H, W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (192, 640)
 import numpy as np
 K = np.array([[0.58 * W, 0, 0.5 * W, 0], [0, 1.92 * H, 0.5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32)
 invK = torch.from_numpy(np.linalg.pinv(K)).to(dev)

@@ -1,0 +1,166 @@
+"""Full mono training step (BASELINE.json configs[2]): ResNet-18 depth network + separate ResNet-18 pose
+network on stock PyTorch / cuDNN, view-synthesis loss either fused (md2_b200) or eager PyTorch ops
+(the oracle restatement of the reference's loss), DDP over N GPUs (NCCL all-reduce of the network
+gradients only; the loss needs no collective).
+
+Driven by bench.py (--workload train_step); not part of the product package.  The networks follow the
+monodepth2 architecture (ResNet encoder, U-Net decoder with reflection-padded 3x3 convolutions + ELU and
+nearest x2 up-sampling, sigmoid disparities at 4 scales; pose decoder on the last encoder feature with a
+0.01 output scale) and are written here from that description, with random initial weights.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torchvision
+
+
+class Conv3x3(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.pad = nn.ReflectionPad2d(1)
+        self.conv = nn.Conv2d(cin, cout, 3)
+
+    def forward(self, x):
+        return self.conv(self.pad(x))
+
+
+class Encoder(nn.Module):
+    def __init__(self, n_images=1):
+        super().__init__()
+        net = torchvision.models.resnet18(weights=None)
+        net.fc = nn.Identity()  # unused head: no parameters without gradients under DDP
+        if n_images > 1:
+            net.conv1 = nn.Conv2d(3 * n_images, 64, 7, 2, 3, bias=False)
+        self.net = net
+        self.ch = [64, 64, 128, 256, 512]
+
+    def forward(self, x):
+        n = self.net
+        x = (x - 0.45) / 0.225
+        f0 = n.relu(n.bn1(n.conv1(x)))
+        f1 = n.layer1(n.maxpool(f0))
+        f2 = n.layer2(f1)
+        f3 = n.layer3(f2)
+        f4 = n.layer4(f3)
+        return [f0, f1, f2, f3, f4]
+
+
+class DepthDecoder(nn.Module):
+    def __init__(self, enc_ch, scales=range(4)):
+        super().__init__()
+        dec = [16, 32, 64, 128, 256]
+        self.scales = list(scales)
+        self.up0, self.up1, self.head = nn.ModuleDict(), nn.ModuleDict(), nn.ModuleDict()
+        for i in range(4, -1, -1):
+            cin = enc_ch[-1] if i == 4 else dec[i + 1]
+            self.up0[str(i)] = Conv3x3(cin, dec[i])
+            self.up1[str(i)] = Conv3x3(dec[i] + (enc_ch[i - 1] if i > 0 else 0), dec[i])
+        for s in self.scales:
+            self.head[str(s)] = Conv3x3(dec[s], 1)
+
+    def forward(self, feats):
+        out = {}
+        x = feats[-1]
+        for i in range(4, -1, -1):
+            x = F.elu(self.up0[str(i)](x))
+            x = F.interpolate(x, scale_factor=2, mode="nearest")
+            if i > 0:
+                x = torch.cat([x, feats[i - 1]], 1)
+            x = F.elu(self.up1[str(i)](x))
+            if i in self.scales:
+                out[("disp", i)] = torch.sigmoid(self.head[str(i)](x))
+        return out
+
+
+class PoseDecoder(nn.Module):
+    def __init__(self, cin):
+        super().__init__()
+        self.squeeze = nn.Conv2d(cin, 256, 1)
+        self.c0 = nn.Conv2d(256, 256, 3, 1, 1)
+        self.c1 = nn.Conv2d(256, 256, 3, 1, 1)
+        self.c2 = nn.Conv2d(256, 12, 1)
+
+    def forward(self, f):
+        x = F.relu(self.squeeze(f))
+        x = F.relu(self.c0(x))
+        x = F.relu(self.c1(x))
+        x = self.c2(x).mean(3).mean(2)
+        x = 0.01 * x.view(-1, 2, 1, 6)
+        return x[..., :3], x[..., 3:]
+
+
+class MonoNets(nn.Module):
+    """The four networks behind one module so that a single DDP wrapper covers them."""
+
+    def __init__(self):
+        super().__init__()
+        self.enc = Encoder(1)
+        self.dec = DepthDecoder(self.enc.ch)
+        self.pose_enc = Encoder(2)
+        self.pose_dec = PoseDecoder(512)
+
+    def forward(self, inputs, frame_ids):
+        outputs = self.dec(self.enc(inputs[("color_aug", 0, 0)]))
+        for f in frame_ids[1:]:
+            pair = [inputs[("color_aug", f, 0)], inputs[("color_aug", 0, 0)]] if f < 0 else \
+                   [inputs[("color_aug", 0, 0)], inputs[("color_aug", f, 0)]]
+            aa, tr = self.pose_dec(self.pose_enc(torch.cat(pair, 1))[-1])
+            outputs[("axisangle", f)] = aa[:, 0].contiguous()
+            outputs[("translation", f)] = tr[:, 0].contiguous()
+        return outputs
+
+
+def synthetic_batch(B, H, W, frame_ids, seed, device):
+    import md2_b200.synthetic as syn
+    inputs, _ = syn.make_batch(B, H, W, frame_ids, 4, seed, "iid", device=device, requires_grad=False)
+    for f in frame_ids:
+        inputs[("color_aug", f, 0)] = inputs[("color", f, 0)]
+    return inputs
+
+
+def make_step(loss_impl, B, H, W, frame_ids, device, ddp):
+    """Returns (step_fn, images_per_step).  loss_impl: 'fused' (md2_b200) or 'eager' (PyTorch ops)."""
+    from types import SimpleNamespace
+    nets = MonoNets().to(device)
+    model = nn.parallel.DistributedDataParallel(nets, device_ids=[device.index]) if ddp else nets
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    batches = [synthetic_batch(B, H, W, frame_ids, s, device) for s in range(2)]
+    cfg = SimpleNamespace(frame_ids=frame_ids, scales=range(4), height=H, width=W, min_depth=0.1, max_depth=100.0,
+                          pose_type="separate", use_automasking=True, disp_smoothness=1e-3)
+    if loss_impl == "fused":
+        from md2_b200.compute import compute
+        from md2_b200 import functional as F_
+        comp = compute(cfg, device)
+
+        def loss_fn(inputs, outputs):
+            for f in frame_ids[1:]:
+                outputs[("c2c", f, 0)] = F_.param2matrix(outputs[("axisangle", f)],
+                                                         outputs[("translation", f)], invert=(f < 0))
+            comp.image2warping(inputs, outputs, None)
+            return comp.compute_loss(inputs, outputs, None)["loss"]
+    else:
+        from oracle import oracle_torch as O  # eager PyTorch restatement of the reference loss (baseline leg)
+
+        def loss_fn(inputs, outputs):
+            Ts = [O.pose_matrix(outputs[("axisangle", f)], outputs[("translation", f)],
+                                invert=(f < 0)) for f in frame_ids[1:]]
+            return O.view_synthesis_loss(inputs[("color", 0, 0)], [inputs[("color", f, 0)] for f in frame_ids[1:]],
+                                         [outputs[("disp", s)] for s in range(4)],
+                                         [inputs[("color", 0, s)] for s in range(4)], inputs[("K", 0)],
+                                         inputs[("inv_K", 0)], Ts)["loss"]
+
+    state = {"i": 0}
+
+    def step():
+        inputs = batches[state["i"] % len(batches)]
+        state["i"] += 1
+        outputs = model(inputs, frame_ids)
+        loss = loss_fn(inputs, outputs)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    return step, B
