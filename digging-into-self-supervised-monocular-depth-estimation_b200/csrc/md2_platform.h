@@ -48,6 +48,45 @@ MD2_FN uint8_t ld_ro(const uint8_t* p) { return *p; }
 MD2_FN void atomic_add(float* p, float v) { *p += v; }
 #endif
 
+// ---- packed pairs: two independent fp32 lanes per instruction (add/mul/fma.rn.f32x2 on sm_100) ----
+// Used to evaluate two source frames at once; every lane is rounded exactly like the scalar op.
+#if MD2_DEVICE_BUILD
+typedef float2 f2;
+MD2_FN f2 mk2(float a, float b) { return make_float2(a, b); }
+// Inline PTX with explicit .rn: nvcc contracts __fmul2_rn + __fadd2_rn into FFMA2 (observed in SASS),
+// which would change the rounding sequence; PTX-level .rn operations are never fused.
+MD2_FN unsigned long long f2_bits(f2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
+MD2_FN f2 bits_f2(unsigned long long v) { return *reinterpret_cast<f2*>(&v); }
+MD2_FN f2 fadd2(f2 a, f2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(d);
+}
+// ptxas (12.9) fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even though both carry .rn (the scalar forms are
+// never fused).  A product written as fma(a, b, +0) cannot be simplified to a mul (it differs for -0) and so
+// cannot be fused with a following add; it rounds exactly like the mul (a -0 product becomes +0).
+MD2_FN f2 fmul2(f2 a, f2 b) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(0ull));
+  return bits_f2(d);
+}
+MD2_FN f2 ffma2(f2 a, f2 b, f2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return bits_f2(d);
+}
+#else
+struct f2 {
+  float x, y;
+};
+MD2_FN f2 mk2(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
+MD2_FN f2 fadd2(f2 a, f2 b) { return mk2(a.x + b.x, a.y + b.y); }
+MD2_FN f2 fmul2(f2 a, f2 b) { return mk2(a.x * b.x, a.y * b.y); }
+MD2_FN f2 ffma2(f2 a, f2 b, f2 c) { return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+MD2_FN f2 bc2(float a) { return mk2(a, a); }
+MD2_FN f2 fsub2(f2 a, f2 b) { return ffma2(b, bc2(-1.0f), a); }  // a - b, exact product, one rounding
+
 MD2_HD int imin(int a, int b) { return a < b ? a : b; }
 MD2_HD int imax(int a, int b) { return a > b ? a : b; }
 
