@@ -5,33 +5,20 @@
 //                              smoothness (model_loss.py:77-88,112-116); zero-fills the
 //                              gradient buffers when a backward follows;
 //   2. tile_kernel<S, BWD>     one CTA per 32x16 image tile, all scales and sources
-//                              (md2_tile.cuh); the backward build appends one CTA per
-//                              smoothness row band for the smoothness gradient;
+//                              (md2_tile.cuh);
 //   3. finalize_kernel         fixed-order reduction of the per-CTA partials -> loss,
-//                              dL/dT = K^T dL/dP.
+//                              dL/dT = K^T dL/dP; gradient of the smoothness term.
 #include <cuda_runtime.h>
 
 #include "md2_host.h"
 
 namespace md2 {
 
-// grid (tiles_x, tiles_y, B + extra): z < B are image tiles; the extra z-layers of the backward build
-// enumerate the smoothness row bands
+// grid (tiles_x, tiles_y, B): one CTA per image tile
 template <class TK, bool DBG>
 __global__ void __launch_bounds__(TK::NT, TK::BWD ? MD2_MINB : 1) tile_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
-  if ((int)blockIdx.z >= p.B) {
-    if (TK::BWD) {
-      const int blk = ((blockIdx.z - p.B) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-      if (blk < p.B * smooth_total(p.ns)) {
-        const SmoothBand k = smooth_band(p, blk);
-        const float gl = p.grad_loss_dev ? __ldg(p.grad_loss_dev) : p.grad_loss_host;
-        smooth_bwd_thread(p, k, tid, TK::NT, gl);
-      }
-    }
-    return;
-  }
   typename TK::Ctx c;
   TK::make_ctx(c, p, sm, blockIdx.x, blockIdx.y, blockIdx.z);
   typename TK::Regs regs;
@@ -73,7 +60,9 @@ struct GradTPtrs {
   float* p[kMaxS];
 };
 
-// block 0: the scalar loss; blocks 1 + (f * B + b): dL/dT_f[b] = K_b^T (sum over the image's tiles of dL/dP)
+// block 0: the scalar loss; blocks 1 + (f * B + b): dL/dT_f[b] = K_b^T (sum over the image's tiles of dL/dP);
+// the remaining blocks: gradient of the smoothness term, one per row band (atomics into grad_disp, which the
+// tile kernel has finished writing by then)
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ Params p, float* loss, GradTPtrs gT,
                                                        int want_grad_T) {
   __shared__ double red[256];
@@ -82,7 +71,35 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ P
   const int t = threadIdx.x;
   if (blockIdx.x == 0) {
     if (!loss) return;
-    red[t] = finalize_loss_partial(p, t, 256);
+    // photometric part: per-CTA partial sums, thread-strided in double
+    double acc = 0.0;
+    const double inv_n = 1.0 / ((double)p.B * p.H * p.W);
+    for (int i = t; i < p.n_tiles * kMaxScales; i += 256)
+      if ((i % kMaxScales) < p.ns) acc += (double)p.tile_loss[i] * inv_n;
+    // smoothness part: one warp per (scale, image), lanes stride the row bands, fixed-order shuffle tree
+    const int warp = t >> 5, lane = t & 31;
+    for (int pair = warp; pair < p.ns * p.B; pair += 8) {
+      const int s = pair / p.B, b = pair - s * p.B;
+      const float* part = p.smooth_part + ((size_t)b * smooth_total(p.ns) + smooth_offset(s)) * 3;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      for (int ch = lane; ch < smooth_chunks(s); ch += 32) {
+        a0 += part[ch * 3 + 0];
+        a1 += part[ch * 3 + 1];
+        a2 += part[ch * 3 + 2];
+      }
+      a0 = warp_sum(a0);
+      a1 = warp_sum(a1);
+      a2 = warp_sum(a2);
+      if (lane == 0) {
+        const int hs = p.H >> s, ws = p.W >> s;
+        const double inv = 1.0 / ((double)a0 / ((double)hs * ws) + 1e-7);
+        double sm = 0.0;
+        if (ws > 1) sm += inv * a1 / ((double)p.B * hs * (ws - 1));
+        if (hs > 1) sm += inv * a2 / ((double)p.B * (hs - 1) * ws);
+        acc += (double)p.lambda * sm / (double)(1 << s);
+      }
+    }
+    red[t] = acc / (double)p.ns;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {  // fixed-shape tree: deterministic
       if (t < o) red[t] += red[t + o];
@@ -92,6 +109,24 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ P
     return;
   }
   if (!want_grad_T) return;
+  if ((int)blockIdx.x >= 1 + p.B * p.S) {
+    const SmoothBand k = smooth_band(p, blockIdx.x - 1 - p.B * p.S);
+    const float gl = p.grad_loss_dev ? __ldg(p.grad_loss_dev) : p.grad_loss_host;
+    // per-image statistics once per block (fixed-order sum over the row bands), then the band's pixels
+    if (t < 3) {
+      const float* part = p.smooth_part + ((size_t)k.b * smooth_total(p.ns) + smooth_offset(k.s)) * 3;
+      float acc = 0.f;
+      for (int ch = 0; ch < smooth_chunks(k.s); ++ch) acc += part[ch * 3 + t];
+      dPs[t] = acc;
+    }
+    __syncthreads();
+    SmoothStats st;
+    st.inv = 1.0f / (dPs[0] / (float)(k.hs * k.ws) + 1e-7f);
+    st.sx = dPs[1];
+    st.sy = dPs[2];
+    smooth_bwd_thread(p, k, st, t, 256, gl);
+    return;
+  }
   const int fb = blockIdx.x - 1;
   const int b = fb % p.B, f = fb / p.B;
   if (f >= p.S || gT.p[f] == nullptr) return;
@@ -147,9 +182,7 @@ static cudaError_t launch_tiles_impl(const Params& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int per_layer = p.tiles_x * p.tiles_y;
-  const int extra = TK::BWD ? (p.B * smooth_total(p.ns) + per_layer - 1) / per_layer : 0;
-  const dim3 grid(p.tiles_x, p.tiles_y, p.B + extra);
+  const dim3 grid(p.tiles_x, p.tiles_y, p.B);
   if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
   tile_kernel<TK, DBG><<<grid, TK::NT, TK::SMEM_BYTES, st>>>(p);
   if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
@@ -214,7 +247,7 @@ static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs*
   if (ce != cudaSuccess) return (int)ce;
   GradTPtrs gT;
   for (int f = 0; f < kMaxS; ++f) gT.p[f] = (g && f < cfg->S) ? g->grad_T[f] : nullptr;
-  finalize_kernel<<<1 + (mode != kForward ? p.B * p.S : 0), 256, 0, st>>>(p, mode == kBackward ? nullptr : out->loss, gT,
+  finalize_kernel<<<1 + (mode != kForward ? p.B * p.S + p.B * smooth_total(p.ns) : 0), 256, 0, st>>>(p, mode == kBackward ? nullptr : out->loss, gT,
                                                                             mode != kForward);
   ce = cudaGetLastError();
   return ce == cudaSuccess ? 0 : (int)ce;

@@ -77,7 +77,8 @@ static void run_smooth_backward(const Params& p) {
   const float gl = p.grad_loss_dev ? *p.grad_loss_dev : p.grad_loss_host;
   for (int blk = 0; blk < p.B * smooth_total(p.ns); ++blk) {
     const SmoothBand k = smooth_band(p, blk);
-    for (int tid = 0; tid < nt; ++tid) smooth_bwd_thread(p, k, tid, nt, gl);
+    const SmoothStats st = smooth_stats(p, k.s, k.b);
+    for (int tid = 0; tid < nt; ++tid) smooth_bwd_thread(p, k, st, tid, nt, gl);
   }
 }
 
