@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(TK::NT, TK::BWD ? MD2_MINB : 1) tile_kernel(co
       TK::phase_c(c, s, tid, regs);
       __syncthreads();
       TK::phase_d1(c, s, tid);
-      __syncthreads();
-      TK::phase_d2(c, s, tid);
+      if (s > 0) {  // scale 0 has no second pass
+        __syncthreads();
+        TK::phase_d2(c, s, tid);
+      }
     }
   }
   TK::epilogue1(c, tid, regs);
