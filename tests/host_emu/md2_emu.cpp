@@ -16,7 +16,9 @@ using namespace md2;
 
 template <class TK>
 static void run_tiles(const Params& p) {
-  std::vector<float> sm(TK::SMEM_FLOATS + 64, 0.f);
+  // the host build keeps one reduction row per thread, which may exceed the aliased warped-tile buffer:
+  // give the arena enough room behind OFF_RED (everything after it is dead in the epilogue)
+  std::vector<float> sm(TK::OFF_RED + TK::NT * TK::NRED + TK::SMEM_FLOATS + 64, 0.f);
   std::vector<typename TK::Regs> regs(TK::NT);
   for (int tile = 0; tile < p.n_tiles; ++tile) {
     typename TK::Ctx c;
