@@ -8,23 +8,122 @@
 //                              (md2_tile.cuh);
 //   3. finalize_kernel         fixed-order reduction of the per-CTA partials -> loss,
 //                              dL/dT = K^T dL/dP; gradient of the smoothness term.
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime (no -lcuda)
 #include <cuda_runtime.h>
+
+#include <stdlib.h>
 
 #include "md2_host.h"
 
 namespace md2 {
 
+// ---------------------------------------------------------------------------------------- TMA
+// Tensor maps over the NCHW fp32 images: dims (W, H, 3, B), box (R2P, R2H, 3, 1) = one tile with its halo,
+// all three channels, out-of-image elements zero-filled.  The box x-origin is a multiple of 4 pixels: TMA
+// needs a 16-byte aligned start in global memory (an unaligned start raises an illegal-instruction error).
+struct alignas(64) TmaMaps {
+  CUtensorMap target;
+  CUtensorMap src[kMaxS];
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static bool make_image_map(CUtensorMap* m, const float* img, int B, int H, int W, int box_w, int box_h) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || ((uintptr_t)img & 15) != 0 || (W & 3) != 0 || (box_w & 3) != 0 || box_w > 256 || box_h > 256) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 3, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_tile(float* dst, const CUtensorMap* map, int x, int y, int b, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_addr(dst)), "l"((uint64_t)map), "r"(x), "r"(y), "r"(0), "r"(b), "r"(mbar)
+      : "memory");
+}
+
+// Stage the target tile (+ halo) and, for the identity loss, the raw source tiles with TMA.
+template <class TK>
+__device__ __forceinline__ void tma_stage_tiles(const typename TK::Ctx& c, const Params& p, const TmaMaps& maps, float* sm,
+                                                int tid) {
+  const uint32_t mbar = smem_addr(sm + TK::OFF_MBAR);
+  const bool need_src = p.automask && !p.use_saved_k;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)(TK::R2S * 3 * sizeof(float)) * (1u + (need_src ? (uint32_t)TK::S : 0u));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    // the box starts XO pixels left of the halo so that its first element is 16-byte aligned in global memory
+    tma_load_tile(sm + TK::OFF_T, &maps.target, c.tx0 - TK::HB - TK::XO, c.ty0 - TK::HB, c.b, mbar);
+    if (need_src)
+      for (int f = 0; f < TK::S; ++f)
+        tma_load_tile(sm + TK::OFF_W + f * TK::WS, &maps.src[f], c.tx0 - TK::HB - TK::XO, c.ty0 - TK::HB, c.b, mbar);
+  }
+  __syncthreads();  // the barrier is initialised (and armed) before anybody polls it
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  // bounded poll: a TMA fault must abort the kernel, never hang the GPU
+#pragma unroll 1
+  for (int it = 0; it < (1 << 24); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
 // grid (tiles_x, tiles_y, B): one CTA per image tile
 template <class TK, bool DBG>
-__global__ void __launch_bounds__(TK::NT, TK::BWD ? MD2_MINB : 1) tile_kernel(const __grid_constant__ Params p) {
-  extern __shared__ __align__(16) float sm[];
+__global__ void __launch_bounds__(TK::NT, TK::BWD ? MD2_MINB : 1)
+    tile_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps maps) {
+  extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x;
   typename TK::Ctx c;
   TK::make_ctx(c, p, sm, blockIdx.x, blockIdx.y, blockIdx.z);
   typename TK::Regs regs;
   TK::init_regs(regs);
-  TK::setup(c, tid);
-  TK::load_tiles(c, tid);
+  if (p.use_tma) {
+    // TMA: one thread issues the box loads, everybody computes K.T meanwhile, then waits on the mbarrier
+    tma_stage_tiles<TK>(c, p, maps, sm, tid);
+    TK::setup(c, tid);
+    mbar_wait(smem_addr(sm + TK::OFF_MBAR), 0);
+    TK::patch_border(c, tid);  // reflection at the image border (TMA zero-fills)
+  } else {
+    TK::setup(c, tid);
+    TK::load_tiles(c, tid);
+  }
   __syncthreads();
   TK::prologue_windows(c, tid);
   __syncthreads();
@@ -174,6 +273,7 @@ __global__ void debug_div_kernel(int n, const float* num, const float* den, floa
 }
 
 static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+static bool g_tma_enabled = true;  // MD2_NO_TMA=1 in the environment disables the TMA path (A/B measurement)
 
 template <class TK, bool DBG>
 static cudaError_t launch_tiles_impl(const Params& p, cudaStream_t st) {
@@ -185,8 +285,15 @@ static cudaError_t launch_tiles_impl(const Params& p, cudaStream_t st) {
     attr_set = true;
   }
   const dim3 grid(p.tiles_x, p.tiles_y, p.B);
+  // TMA staging of the target / raw source tiles when the layout allows it (16-byte aligned bases, W % 4 == 0,
+  // box row a multiple of 16 bytes); otherwise the kernel loads the tiles with plain coalesced loads
+  TmaMaps maps;
+  Params q = p;
+  q.use_tma = g_tma_enabled && (TK::TW % 4 == 0) && make_image_map(&maps.target, p.target, p.B, p.H, p.W, TK::R2P, TK::R2H);
+  for (int f = 0; f < TK::S && q.use_tma; ++f)
+    q.use_tma = make_image_map(&maps.src[f], p.src[f], p.B, p.H, p.W, TK::R2P, TK::R2H);
   if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
-  tile_kernel<TK, DBG><<<grid, TK::NT, TK::SMEM_BYTES, st>>>(p);
+  tile_kernel<TK, DBG><<<grid, TK::NT, TK::SMEM_BYTES, st>>>(q, maps);
   if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
   return cudaGetLastError();
 }
@@ -215,9 +322,19 @@ static cudaError_t dispatch_tiles(const Params& p, cudaStream_t st) {
   }
 }
 
+static void read_env_once() {
+  static bool done = false;
+  if (!done) {
+    done = true;
+    const char* e = getenv("MD2_NO_TMA");
+    if (e && e[0] == '1') g_tma_enabled = false;
+  }
+}
+
 static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out, const md2_grads* g,
                     float grad_loss, const float* grad_loss_dev, const uint8_t* saved_k, void* workspace,
                     md2_stream_t stream, Mode mode, const Params* tweak) {
+  read_env_once();
   int e = validate_cfg(cfg);
   if (e) return e;
   e = validate_inputs(cfg, in);

@@ -26,7 +26,12 @@ static void run_tiles(const Params& p) {
     TK::make_ctx(c, p, sm.data(), t % p.tiles_x, t / p.tiles_x, tile / per_img);
     PHASE(TK::init_regs(regs[tid]));
     PHASE(TK::setup(c, tid));
-    PHASE(TK::load_tiles(c, tid));
+    if (p.use_tma) {
+      PHASE(TK::load_tiles_zero_fill(c, tid));
+      PHASE(TK::patch_border(c, tid));
+    } else {
+      PHASE(TK::load_tiles(c, tid));
+    }
     PHASE(TK::prologue_windows(c, tid));
     for (int s = 0; s < p.ns; ++s) {
       PHASE(TK::template phase_a<true>(c, s, tid));
@@ -113,6 +118,7 @@ static int run(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out,
   fill_params(p, cfg, in, out, g, ws.data(), mode);
   p.grad_loss_host = grad_loss;
   p.saved_k = saved_k;
+  p.use_tma = getenv("MD2_EMU_TMA") != nullptr;
   if (tweak) {
     p.dbg_coords = tweak->dbg_coords;
     p.dbg_warped = tweak->dbg_warped;

@@ -138,3 +138,18 @@ def test_emu_pose_matches_golden():
         ga, gt = emu.pose_backward(aa, tr, inv, cot[k])
         assert torch.allclose(ga.view(-1, 1, 3), torch.from_numpy(z[f"grad_aa{k}"]), rtol=1e-4, atol=1e-5)
         assert torch.allclose(gt.view(-1, 1, 3), torch.from_numpy(z[f"grad_tr{k}"]), rtol=1e-4, atol=1e-5)
+
+
+def test_emu_tma_style_zero_fill_and_border_patch_equals_reflected_loads(monkeypatch):
+    """The device stages the target / source tiles with TMA (zero fill outside the image) and patches the
+    reflection halo afterwards; the host emulation reproduces that path when MD2_EMU_TMA is set."""
+    args = synth_args(2, 40, 72, [0, -1, 1], True, "iid", 31)
+    ref = emu.forward_backward(args)
+    monkeypatch.setenv("MD2_EMU_TMA", "1")
+    tma = emu.forward_backward(args)
+    fwd = emu.forward(args)
+    for k in ("per_pixel", "argmin", "depth"):
+        assert torch.equal(ref[k], tma[k]), k
+        assert torch.equal(ref[k], fwd[k]), k
+    for s in range(4):
+        assert torch.equal(ref["grad_disp"][s], tma["grad_disp"][s])
