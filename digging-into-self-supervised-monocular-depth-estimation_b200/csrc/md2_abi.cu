@@ -23,7 +23,6 @@ namespace md2 {
 // needs a 16-byte aligned start in global memory (an unaligned start raises an illegal-instruction error).
 struct alignas(64) TmaMaps {
   CUtensorMap target;
-  CUtensorMap src[kMaxS];
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -65,22 +64,18 @@ __device__ __forceinline__ void tma_load_tile(float* dst, const CUtensorMap* map
       : "memory");
 }
 
-// Stage the target tile (+ halo) and, for the identity loss, the raw source tiles with TMA.
+// Stage the target tile (+ halo) with TMA.
 template <class TK>
 __device__ __forceinline__ void tma_stage_tiles(const typename TK::Ctx& c, const Params& p, const TmaMaps& maps, float* sm,
                                                 int tid) {
   const uint32_t mbar = smem_addr(sm + TK::OFF_MBAR);
-  const bool need_src = p.automask && !p.use_saved_k;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t bytes = (uint32_t)(TK::R2S * 3 * sizeof(float)) * (1u + (need_src ? (uint32_t)TK::S : 0u));
+    const uint32_t bytes = (uint32_t)(TK::R2S * 3 * sizeof(float));
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
     // the box starts XO pixels left of the halo so that its first element is 16-byte aligned in global memory
     tma_load_tile(sm + TK::OFF_T, &maps.target, c.tx0 - TK::HB - TK::XO, c.ty0 - TK::HB, c.b, mbar);
-    if (need_src)
-      for (int f = 0; f < TK::S; ++f)
-        tma_load_tile(sm + TK::OFF_W + f * TK::WS, &maps.src[f], c.tx0 - TK::HB - TK::XO, c.ty0 - TK::HB, c.b, mbar);
   }
   __syncthreads();  // the barrier is initialised (and armed) before anybody polls it
 }
@@ -118,6 +113,7 @@ __global__ void __launch_bounds__(TK::NT, TK::BWD ? MD2_MINB : 1)
     // TMA: one thread issues the box loads, everybody computes K.T meanwhile, then waits on the mbarrier
     tma_stage_tiles<TK>(c, p, maps, sm, tid);
     TK::setup(c, tid);
+    TK::load_sources(c, tid);  // raw sources for the identity loss, overlapping the TMA transfer
     mbar_wait(smem_addr(sm + TK::OFF_MBAR), 0);
     TK::patch_border(c, tid);  // reflection at the image border (TMA zero-fills)
   } else {
@@ -290,8 +286,6 @@ static cudaError_t launch_tiles_impl(const Params& p, cudaStream_t st) {
   TmaMaps maps;
   Params q = p;
   q.use_tma = g_tma_enabled && (TK::TW % 4 == 0) && make_image_map(&maps.target, p.target, p.B, p.H, p.W, TK::R2P, TK::R2H);
-  for (int f = 0; f < TK::S && q.use_tma; ++f)
-    q.use_tma = make_image_map(&maps.src[f], p.src[f], p.B, p.H, p.W, TK::R2P, TK::R2H);
   if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
   tile_kernel<TK, DBG><<<grid, TK::NT, TK::SMEM_BYTES, st>>>(q, maps);
   if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);

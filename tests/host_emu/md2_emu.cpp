@@ -28,6 +28,7 @@ static void run_tiles(const Params& p) {
     PHASE(TK::setup(c, tid));
     if (p.use_tma) {
       PHASE(TK::load_tiles_zero_fill(c, tid));
+      PHASE(TK::load_sources(c, tid));
       PHASE(TK::patch_border(c, tid));
     } else {
       PHASE(TK::load_tiles(c, tid));
