@@ -223,6 +223,31 @@ def run_ours(args):
     lib.md2_set_tile_kernel_events(None, None)
     kernel_ms = sum(kms) / len(kms)
 
+    # ---- the two split entry points (validation forward; stand-alone backward), for reference ----------
+    def time_calls(fn, n=20):
+        fn(0)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(n):
+            fn(i)
+        a1.record()
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / n
+
+    def fwd_only(i):
+        prep, cfg, inp, out, g, ws, *_ = sets[i % n_sets]
+        assert lib.md2_loss_forward(C.byref(cfg), C.byref(inp), C.byref(out), C.c_void_p(ws.data_ptr()), stream) == 0
+
+    gl_dev = torch.ones(1, device=dev)
+
+    def bwd_only(i):
+        prep, cfg, inp, out, g, ws, o, *_ = sets[i % n_sets]
+        assert lib.md2_loss_backward(C.byref(cfg), C.byref(inp), C.c_void_p(o["argmin"].data_ptr()),
+                                     C.c_void_p(gl_dev.data_ptr()), C.byref(g), C.c_void_p(ws.data_ptr()), stream) == 0
+
+    fwd_ms, bwd_ms = time_calls(fwd_only), time_calls(bwd_only)
+
     # ---- end-to-end leg: public API, host inputs in pinned memory -------------------------------
     opt = SimpleNamespace(frame_ids=FRAME_IDS, scales=range(NUM_SCALES), height=H, width=W, min_depth=0.1,
                           max_depth=100.0, pose_type="separate", use_automasking=True, disp_smoothness=1e-3)
@@ -307,6 +332,8 @@ def run_ours(args):
                 "api": "md2_b200.compute.compute.image2warping + compute_loss + loss.backward(); inputs from pinned "
                        "host memory on a copy stream (step i+1 uploads while step i computes), loss read back"},
         "gpu_launches": 3 * args.steps,
+        "split_calls_ms": {"md2_loss_forward": fwd_ms, "md2_loss_backward": bwd_ms,
+                           "md2_loss_forward_backward": ms_total / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "md2::tile_kernel<Tile<2,true,32,16,256>>",
                      "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo, "peak_source": peak_src},

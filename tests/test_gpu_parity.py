@@ -238,6 +238,65 @@ def test_compute_dropin_dict_protocol():
         assert norm_rel(outputs[("translation", f)].grad, tr[f].grad) <= 2e-3
 
 
+def test_fused_step_is_cuda_graph_capturable(cl):
+    """The C ABI neither allocates nor synchronises, so a whole step can be captured in a CUDA graph."""
+    import ctypes as C
+    import md2_b200.cabi as cabi
+    args = synth_args(2, 96, 320, [0, -1, 1], True, "smooth", 20)
+    eager = cl.forward_backward(args)
+    a, cfg, inp = cl._prep(args)
+    o = cl._alloc_out(cfg, DEV)
+    gd = [torch.zeros_like(d) for d in a["disps"]]
+    gT = [torch.zeros(cfg.B, 4, 4, device=DEV) for _ in a["Ts"]]
+    ws = cl._ws(cfg, DEV)
+    out = cabi.make_outputs(o["loss"], o["per_pixel"], o["argmin"], o["depth"])
+    g = cabi.make_grads(gd, gT)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            rc = cl.lib.md2_loss_forward_backward(C.byref(cfg), C.byref(inp), C.byref(out), C.byref(g), C.c_float(1.0),
+                                                  C.c_void_p(ws.data_ptr()), C.c_void_p(side.cuda_stream))
+            assert rc == 0
+    for _ in range(3):
+        o["loss"].zero_()
+        graph.replay()
+    torch.cuda.synchronize()
+    assert float(o["loss"]) == pytest.approx(float(eager["loss"]), rel=1e-6)
+    assert torch.equal(o["argmin"], eager["argmin"])
+    for s in range(4):
+        assert norm_rel(gd[s], eager["grad_disp"][s]) <= 1e-5
+
+
+def test_compute_dropin_with_stereo_frame():
+    """frame_ids [0, -1, 1, 's']: inputs["stereo"] is data (processor.py:148-149), no gradient flows to it."""
+    from types import SimpleNamespace
+    import md2_b200.synthetic as syn
+    from md2_b200.compute import compute
+    from md2_b200 import functional as F_
+    from oracle import oracle_torch as O
+    fids = [0, -1, 1, "s"]
+    inputs, outputs = syn.make_batch(2, 64, 96, fids, 4, 21, "smooth", device=DEV)
+    for f in (-1, 1):
+        outputs[("c2c", f, 0)] = F_.param2matrix(outputs[("axisangle", f)], outputs[("translation", f)], invert=(f < 0))
+    opt = SimpleNamespace(frame_ids=fids, scales=range(4), height=64, width=96, min_depth=0.1, max_depth=100.0,
+                          pose_type="separate", use_automasking=True, disp_smoothness=1e-3)
+    noise = [n.to(DEV) for n in syn.make_noise(2, 3, 64, 96, 4, 21)]
+    c = compute(opt, DEV)
+    c.image2warping(inputs, outputs, None, noise=noise)
+    c.compute_loss(inputs, outputs, None)
+    outputs["loss"].backward()
+    Ts = [outputs[("c2c", -1, 0)].detach(), outputs[("c2c", 1, 0)].detach(), inputs["stereo"]]
+    ref = O.view_synthesis_loss(inputs[("color", 0, 0)], [inputs[("color", f, 0)] for f in fids[1:]],
+                                [outputs[("disp", s)].detach() for s in range(4)],
+                                [inputs[("color", 0, s)] for s in range(4)], inputs[("K", 0)], inputs[("inv_K", 0)],
+                                Ts, noise=noise)
+    assert float(outputs["loss"]) == pytest.approx(float(ref["loss"]), rel=1e-5)
+    assert inputs["stereo"].grad is None
+    assert torch.isfinite(outputs[("disp", 0)].grad).all()
+
+
 def test_pose_kernel_matches_golden_and_torch():
     from md2_b200 import functional as F_
     z = np.load(f"{GOLDEN_DIR}/pose.npz")
