@@ -255,52 +255,65 @@ def run_ours(args):
     # only what the path consumes travels: target pyramid, scale-0 sources, K / inv_K, disparities, poses
     def consumed(k):
         return (k[0] == "color" and (k[2] == 0 or k[1] == 0)) or k[0] in ("K", "inv_K")
+    # one pinned staging buffer per batch: a single H2D copy per step, the dict entries are views of it
     pinned = []
     for inputs, outputs in host:
-        pin_in = {k: v.pin_memory() for k, v in inputs.items() if consumed(k)}
-        pin_out = {k: v.pin_memory() for k, v in outputs.items() if k[0] in ("disp", "c2c")}
-        pinned.append((pin_in, pin_out))
-    h2d_bytes = sum(v.numel() * v.element_size() for d in pinned[0] for v in d.values())
+        items = [(("in", k), v) for k, v in inputs.items() if consumed(k)] + \
+                [(("out", k), v) for k, v in outputs.items() if k[0] in ("disp", "c2c")]
+        total = sum((v.numel() + 63) // 64 * 64 for _, v in items)
+        flat = torch.empty(total, dtype=torch.float32).pin_memory()
+        layout, off = [], 0
+        for key, v in items:
+            flat[off:off + v.numel()].copy_(v.reshape(-1))
+            layout.append((key, off, v.numel(), tuple(v.shape)))
+            off += (v.numel() + 63) // 64 * 64
+        pinned.append((flat, layout))
+    h2d_bytes = pinned[0][0].numel() * 4
     loss_host = [torch.empty((), pin_memory=True) for _ in range(2)]
     # two-stage pipeline: a copy stream uploads batch i+1 while the compute stream runs step i (every step
     # still pays its own H2D copy and loss read-back inside the timed region; they overlap with compute)
     copy_stream = torch.cuda.Stream(device=dev)
-    main_stream = torch.cuda.current_stream()
+    main_stream = torch.cuda.Stream(device=dev)
     staged = {}
 
     def upload(i):
-        pin_in, pin_out = pinned[i % n_sets]
+        flat, layout = pinned[i % n_sets]
         with torch.cuda.stream(copy_stream):
-            inputs = {k: v.to(dev, non_blocking=True) for k, v in pin_in.items()}
-            outputs = {k: v.to(dev, non_blocking=True) for k, v in pin_out.items()}
+            dflat = flat.to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        staged[i] = (inputs, outputs, ev)
+        staged[i] = (dflat, layout, ev)
 
     def e2e_step(i, last):
         if i not in staged:
             upload(i)
-        inputs, outputs, ev = staged.pop(i)
+        dflat, layout, ev = staged.pop(i)
         if not last:
             upload(i + 1)
-        main_stream.wait_event(ev)
-        for t in list(inputs.values()) + list(outputs.values()):
-            t.record_stream(main_stream)
-        outputs = {k: v.requires_grad_(True) for k, v in outputs.items()}
-        comp.image2warping(inputs, outputs, None)
-        comp.compute_loss(inputs, outputs, None)
-        outputs["loss"].backward()
-        loss_host[i & 1].copy_(outputs["loss"].detach(), non_blocking=True)
+        with torch.cuda.stream(main_stream):
+            main_stream.wait_event(ev)
+            dflat.record_stream(main_stream)
+            inputs, outputs = {}, {}
+            for (kind, key), off, n, shape in layout:
+                v = dflat[off:off + n].view(shape)
+                if kind == "in":
+                    inputs[key] = v
+                else:
+                    outputs[key] = v.requires_grad_(True)
+            comp.image2warping(inputs, outputs, None)
+            comp.compute_loss(inputs, outputs, None)
+            outputs["loss"].backward()
+            loss_host[i & 1].copy_(outputs["loss"].detach(), non_blocking=True)
         return outputs
 
     for i in range(args.warmup):
         e2e_step(i, i == args.warmup - 1)
     barrier()
     x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    x0.record()
+    x0.record(main_stream)
     for i in range(args.steps):
         e2e_step(i, i == args.steps - 1)
-    x1.record()
+    x1.record(main_stream)
     barrier()
     e2e_ms_total = x0.elapsed_time(x1)
 
@@ -331,7 +344,7 @@ def run_ours(args):
                 "ms_per_step": e2e_ms_total / args.steps,
                 "api": "md2_b200.compute.compute.image2warping + compute_loss + loss.backward(); inputs from pinned "
                        "host memory on a copy stream (step i+1 uploads while step i computes), loss read back"},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 5 * args.steps,
         "split_calls_ms": {"md2_loss_forward": fwd_ms, "md2_loss_backward": bwd_ms,
                            "md2_loss_forward_backward": ms_total / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -1,13 +1,15 @@
 // md2_abi.cu - sm_100a kernels and the extern "C" entry points of include/md2_loss.h.
 //
-// Launch structure of one step (3 launches, no host synchronisation, no allocation):
+// Launch structure of one step (5 launches with backward, 3 without; no host synchronisation, no allocation;
+// the smoothness kernels run on a side stream beside the tile kernel):
+//   0. zero_grads_kernel       (backward) zero-fill of the gradient buffers;
 //   1. smooth_forward_kernel   per (scale, image, row band): sums for the mean-normalised
-//                              smoothness (model_loss.py:77-88,112-116); zero-fills the
-//                              gradient buffers when a backward follows;
+//                              smoothness (model_loss.py:77-88,112-116);
+//  1b. smooth_backward_kernel  (backward) gradient of the smoothness term;
 //   2. tile_kernel<S, BWD>     one CTA per 32x16 image tile, all scales and sources
 //                              (md2_tile.cuh);
 //   3. finalize_kernel         fixed-order reduction of the per-CTA partials -> loss,
-//                              dL/dT = K^T dL/dP; gradient of the smoothness term.
+//                              dL/dT = K^T dL/dP.
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime (no -lcuda)
 #include <cuda_runtime.h>
 
@@ -147,19 +149,48 @@ __global__ void __launch_bounds__(256) smooth_forward_kernel(const __grid_consta
   __shared__ float red[8 * 3];
   const SmoothBand k = smooth_band(p, blockIdx.x);
   float v[3];
-  smooth_fwd_thread(p, k, threadIdx.x, 256, zero_grad != 0, v);
+  smooth_fwd_thread(p, k, threadIdx.x, 256, false, v);
+  (void)zero_grad;
   Reduce<256>::stage1(v, 3, threadIdx.x, red);
   __syncthreads();
   if (threadIdx.x < 3) p.smooth_part[(size_t)blockIdx.x * 3 + threadIdx.x] = Reduce<256>::stage2(threadIdx.x, 3, red);
+}
+
+// zero-fill of the gradient buffers (all scales), before anything accumulates into them
+__global__ void __launch_bounds__(256) zero_grads_kernel(const __grid_constant__ Params p) {
+  for (int s = 0; s < p.ns; ++s) {
+    const int n = p.B * (p.H >> s) * (p.W >> s);
+    float* g = p.grad_disp[s];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) g[i] = 0.f;
+  }
+}
+
+// gradient of the smoothness term, one block per row band (atomics into grad_disp; independent of the
+// tile kernel, so it runs beside it on the side stream)
+__global__ void __launch_bounds__(256) smooth_backward_kernel(const __grid_constant__ Params p) {
+  __shared__ float stat[3];
+  const int t = threadIdx.x;
+  const SmoothBand k = smooth_band(p, blockIdx.x);
+  const float gl = p.grad_loss_dev ? __ldg(p.grad_loss_dev) : p.grad_loss_host;
+  if (t < 3) {  // per-image statistics once per block (fixed-order sum over the row bands)
+    const float* part = p.smooth_part + ((size_t)k.b * smooth_total(p.ns) + smooth_offset(k.s)) * 3;
+    float acc = 0.f;
+    for (int ch = 0; ch < smooth_chunks(k.s); ++ch) acc += part[ch * 3 + t];
+    stat[t] = acc;
+  }
+  __syncthreads();
+  SmoothStats st;
+  st.inv = 1.0f / (stat[0] / (float)(k.hs * k.ws) + 1e-7f);
+  st.sx = stat[1];
+  st.sy = stat[2];
+  smooth_bwd_thread(p, k, st, t, 256, gl);
 }
 
 struct GradTPtrs {
   float* p[kMaxS];
 };
 
-// block 0: the scalar loss; blocks 1 + (f * B + b): dL/dT_f[b] = K_b^T (sum over the image's tiles of dL/dP);
-// the remaining blocks: gradient of the smoothness term, one per row band (atomics into grad_disp, which the
-// tile kernel has finished writing by then)
+// block 0: the scalar loss; blocks 1 + (f * B + b): dL/dT_f[b] = K_b^T (sum over the image's tiles of dL/dP)
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ Params p, float* loss, GradTPtrs gT,
                                                        int want_grad_T) {
   __shared__ double red[256];
@@ -206,24 +237,6 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ P
     return;
   }
   if (!want_grad_T) return;
-  if ((int)blockIdx.x >= 1 + p.B * p.S) {
-    const SmoothBand k = smooth_band(p, blockIdx.x - 1 - p.B * p.S);
-    const float gl = p.grad_loss_dev ? __ldg(p.grad_loss_dev) : p.grad_loss_host;
-    // per-image statistics once per block (fixed-order sum over the row bands), then the band's pixels
-    if (t < 3) {
-      const float* part = p.smooth_part + ((size_t)k.b * smooth_total(p.ns) + smooth_offset(k.s)) * 3;
-      float acc = 0.f;
-      for (int ch = 0; ch < smooth_chunks(k.s); ++ch) acc += part[ch * 3 + t];
-      dPs[t] = acc;
-    }
-    __syncthreads();
-    SmoothStats st;
-    st.inv = 1.0f / (dPs[0] / (float)(k.hs * k.ws) + 1e-7f);
-    st.sx = dPs[1];
-    st.sy = dPs[2];
-    smooth_bwd_thread(p, k, st, t, 256, gl);
-    return;
-  }
   const int fb = blockIdx.x - 1;
   const int b = fb % p.B, f = fb / p.B;
   if (f >= p.S || gT.p[f] == nullptr) return;
@@ -269,7 +282,8 @@ __global__ void debug_div_kernel(int n, const float* num, const float* den, floa
 }
 
 static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
-static bool g_tma_enabled = true;  // MD2_NO_TMA=1 in the environment disables the TMA path (A/B measurement)
+static bool g_tma_enabled = true;   // MD2_NO_TMA=1 in the environment disables the TMA path (A/B measurement)
+static bool g_side_enabled = true;  // MD2_NO_SIDE=1 keeps the smoothness kernels on the caller's stream
 
 template <class TK, bool DBG>
 static cudaError_t launch_tiles_impl(const Params& p, cudaStream_t st) {
@@ -316,12 +330,33 @@ static cudaError_t dispatch_tiles(const Params& p, cudaStream_t st) {
   }
 }
 
+// One non-blocking side stream + fork/join events per (host thread, device); created on first use.
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+static SideStream* side_stream() {
+  thread_local SideStream cache[16];
+  thread_local bool ready[16] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!ready[dev]) {
+    if (cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&cache[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&cache[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ready[dev] = true;
+  }
+  return &cache[dev];
+}
+
 static void read_env_once() {
   static bool done = false;
   if (!done) {
     done = true;
     const char* e = getenv("MD2_NO_TMA");
     if (e && e[0] == '1') g_tma_enabled = false;
+    e = getenv("MD2_NO_SIDE");
+    if (e && e[0] == '1') g_side_enabled = false;
   }
 }
 
@@ -353,14 +388,33 @@ static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs*
     p.dbg_source = tweak->dbg_source;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  smooth_forward_kernel<<<p.B * smooth_total(p.ns), 256, 0, st>>>(p, mode != kForward);
-  cudaError_t ce = cudaGetLastError();
-  if (ce != cudaSuccess) return (int)ce;
+  // The smoothness term (forward sums, then its gradient) does not depend on the tile kernel, so it runs on a
+  // side stream beside it (fork / join with events: no host synchronisation, capturable in a CUDA graph).
+  SideStream* side = side_stream();
+  if (!side) return MD2_ERR_NO_DEVICE;
+  cudaError_t ce;
+  if (mode != kForward) {
+    zero_grads_kernel<<<296, 256, 0, st>>>(p);
+    if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
+  }
+  cudaStream_t ss = g_side_enabled ? side->stream : st;
+  if (g_side_enabled) {
+    if ((ce = cudaEventRecord(side->fork, st)) != cudaSuccess) return (int)ce;
+    if ((ce = cudaStreamWaitEvent(ss, side->fork, 0)) != cudaSuccess) return (int)ce;
+  }
+  smooth_forward_kernel<<<p.B * smooth_total(p.ns), 256, 0, ss>>>(p, 0);
+  if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
+  if (mode != kForward) {
+    smooth_backward_kernel<<<p.B * smooth_total(p.ns), 256, 0, ss>>>(p);
+    if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
+  }
+  if (g_side_enabled && (ce = cudaEventRecord(side->join, ss)) != cudaSuccess) return (int)ce;
   ce = mode == kForward ? dispatch_tiles<false>(p, st) : dispatch_tiles<true>(p, st);
   if (ce != cudaSuccess) return (int)ce;
+  if (g_side_enabled && (ce = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return (int)ce;
   GradTPtrs gT;
   for (int f = 0; f < kMaxS; ++f) gT.p[f] = (g && f < cfg->S) ? g->grad_T[f] : nullptr;
-  finalize_kernel<<<1 + (mode != kForward ? p.B * p.S + p.B * smooth_total(p.ns) : 0), 256, 0, st>>>(p, mode == kBackward ? nullptr : out->loss, gT,
+  finalize_kernel<<<1 + (mode != kForward ? p.B * p.S : 0), 256, 0, st>>>(p, mode == kBackward ? nullptr : out->loss, gT,
                                                                             mode != kForward);
   ce = cudaGetLastError();
   return ce == cudaSuccess ? 0 : (int)ce;
@@ -432,8 +486,8 @@ int md2_pose_backward(int n, const float* axisangle, const float* translation, i
 }
 
 int md2_launches_per_step(const md2_cfg* cfg, int with_backward) {
-  (void)with_backward;
-  return validate_cfg(cfg) ? 0 : 3;
+  if (validate_cfg(cfg)) return 0;
+  return with_backward ? 5 : 3;  // [zero grads,] smoothness sums, [smoothness gradient,] tile kernel, finalize
 }
 
 int md2_debug_div(int n, const float* num, const float* den, float* q_div, float* q9, md2_stream_t stream) {

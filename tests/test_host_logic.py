@@ -33,7 +33,8 @@ def test_library_exports_every_declared_symbol(lib):
 def test_workspace_and_validation_without_gpu(lib):
     ok = cabi.make_cfg(12, 192, 640, 2)
     assert lib.md2_workspace_bytes(C.byref(ok)) > 0
-    assert lib.md2_launches_per_step(C.byref(ok), 1) == 3
+    assert lib.md2_launches_per_step(C.byref(ok), 1) == 5
+    assert lib.md2_launches_per_step(C.byref(ok), 0) == 3
     for bad in (cabi.make_cfg(0, 192, 640, 2), cabi.make_cfg(12, 190, 640, 2), cabi.make_cfg(12, 192, 640, 5),
                 cabi.make_cfg(12, 192, 640, 2, num_scales=5), cabi.make_cfg(12, 192, 640, 2, min_depth=0.0)):
         assert lib.md2_workspace_bytes(C.byref(bad)) == 0
