@@ -238,6 +238,29 @@ def test_compute_dropin_dict_protocol():
         assert norm_rel(outputs[("translation", f)].grad, tr[f].grad) <= 2e-3
 
 
+@pytest.mark.parametrize("B,H,W,frame_ids", [
+    (8, 320, 1024, [0, -1, 1, "s"]),        # BASELINE configs[3]: mono+stereo, high resolution, per-GPU batch 8
+    (4, 384, 1280, [0, -1, 1, "s", 2]),     # largest sweep size, four sources
+])
+def test_large_configs_against_oracle(cl, B, H, W, frame_ids):
+    """Full-size configurations of the sweep: loss and argmin against the oracle on the same GPU."""
+    from oracle import oracle_torch as O
+    args = synth_args(B, H, W, frame_ids, True, "iid", 30)
+    out = cl.forward_backward(args)
+    fwd = cl.forward(args)
+    with torch.no_grad():
+        ref = O.view_synthesis_loss(**args)
+    assert float(out["loss"]) == pytest.approx(float(ref["loss"]), rel=1e-6)
+    for s in range(4):
+        assert torch.equal(out["per_pixel"][s], ref["per_pixel"][s]), s
+        assert torch.equal(out["argmin"][s].long(), ref["argmin"][s]), s
+        assert torch.equal(out["depth"][s], ref["depth"][s]), s
+    for k in ("per_pixel", "argmin", "depth"):
+        assert torch.equal(fwd[k], out[k]), k
+    for g in out["grad_disp"] + out["grad_T"]:
+        assert torch.isfinite(g).all()
+
+
 def test_fused_step_is_cuda_graph_capturable(cl):
     """The C ABI neither allocates nor synchronises, so a whole step can be captured in a CUDA graph."""
     import ctypes as C
