@@ -60,67 +60,63 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~2 ms period;
-    nvidia-smi as a fallback)."""
+    """SM clock and throttle reasons sampled DURING the timed region by an `nvidia-smi -lms` subprocess
+    (the profiling recipe's clocks line); samples are kept when their timestamp falls inside the region."""
+
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.sm, self.mx, self.reasons, self.stop_flag = index, [], 0, set(), False
-        self.nv = None
+        self.index, self.proc, self.t0, self.t1 = index, None, None, None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.25)  # let it start sampling before the region begins
         except Exception:
-            self.nv = None
-
-    def _sample_nvml(self):
-        nv = self.nv
-        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
-                          ("hw_thermal_slowdown", 0x40)):
-            if r & bit:
-                self.reasons.add(name)
-
-    def _sample_smi(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                           capture_output=True, text=True, timeout=5)
-        r = [x.strip() for x in o.stdout.strip().split(",")]
-        self.sm.append(float(r[0]))
-        self.mx = max(self.mx, float(r[1]))
-        for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
-            if v.lower().startswith("active"):
-                self.reasons.add(n)
-
-    def _run(self):
-        while not self.stop_flag:
-            try:
-                if self.nv:
-                    self._sample_nvml()
-                    time.sleep(0.002)
-                else:
-                    self._sample_smi()
-            except Exception:
-                time.sleep(0.05)
+            self.proc = None
 
     def __enter__(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
+        self.t0 = time.time()
         return self
 
     def __exit__(self, *a):
-        self.stop_flag = True
-        self.t.join(timeout=6)
+        self.t1 = time.time()
+        time.sleep(0.03)
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.out = self.proc.communicate(timeout=5)[0]
+            except Exception:
+                self.out = ""
+        else:
+            self.out = ""
 
     def summary(self):
-        sm = sorted(self.sm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.mx) if self.mx else None,
-                "reasons": sorted(self.reasons), "samples": len(sm)}
+        import datetime
+        sm, mx, reasons, all_sm = [], 0.0, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.out.splitlines():
+            r = [x.strip() for x in line.split(",")]
+            if len(r) < 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(r[1]), float(r[2])
+            except ValueError:
+                continue
+            mx = max(mx, cmax)
+            all_sm.append(clk)
+            if self.t0 - 0.02 <= ts <= self.t1 + 0.02:
+                sm.append(clk)
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        if not sm:  # region shorter than the sampling period: take the nearest samples
+            sm = all_sm[-3:]
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
 
 
 def make_host_batch(seed):
@@ -275,14 +271,19 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.Stream(device=dev)
     staged = {}
+    dev_bufs = [torch.empty(pinned[0][0].numel(), dtype=torch.float32, device=dev) for _ in range(2)]
+    buf_free = [None, None]  # event recorded on the compute stream when the step using the buffer is enqueued
 
     def upload(i):
         flat, layout = pinned[i % n_sets]
+        j = i & 1
         with torch.cuda.stream(copy_stream):
-            dflat = flat.to(dev, non_blocking=True)
+            if buf_free[j] is not None:
+                copy_stream.wait_event(buf_free[j])  # the step that last read this buffer has finished
+            dev_bufs[j].copy_(flat, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        staged[i] = (dflat, layout, ev)
+        staged[i] = (dev_bufs[j], layout, ev)
 
     def e2e_step(i, last):
         if i not in staged:
@@ -292,7 +293,6 @@ def run_ours(args):
             upload(i + 1)
         with torch.cuda.stream(main_stream):
             main_stream.wait_event(ev)
-            dflat.record_stream(main_stream)
             inputs, outputs = {}, {}
             for (kind, key), off, n, shape in layout:
                 v = dflat[off:off + n].view(shape)
@@ -304,6 +304,8 @@ def run_ours(args):
             comp.compute_loss(inputs, outputs, None)
             outputs["loss"].backward()
             loss_host[i & 1].copy_(outputs["loss"].detach(), non_blocking=True)
+            buf_free[i & 1] = torch.cuda.Event()
+            buf_free[i & 1].record(main_stream)
         return outputs
 
     for i in range(args.warmup):
