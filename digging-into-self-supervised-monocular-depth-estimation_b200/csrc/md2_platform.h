@@ -90,18 +90,4 @@ MD2_FN f2 fsub2(f2 a, f2 b) { return ffma2(b, bc2(-1.0f), a); }  // a - b, exact
 MD2_HD int imin(int a, int b) { return a < b ? a : b; }
 MD2_HD int imax(int a, int b) { return a > b ? a : b; }
 
-// ---- counter-based N(0,1) for the auto-mask tie-breaker when no noise is supplied ----
-MD2_FN uint64_t splitmix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
-}
-MD2_FN float gauss_from_counter(uint64_t seed, uint64_t counter) {
-  const uint64_t h = splitmix64(seed ^ splitmix64(counter));
-  const float u1 = ((float)((h >> 40) & 0xFFFFFF) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
-  const float u2 = (float)((h >> 8) & 0xFFFFFF) * (1.0f / 16777216.0f);            // [0,1)
-  return sqrtf(-2.0f * logf(u1)) * cosf(6.28318530717958647692f * u2);
-}
-
 }  // namespace md2
