@@ -43,11 +43,11 @@ def _run(cmd, verbose):
 
 
 def build_cuda_library(force=False, verbose=False, ptxas_verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("md2_abi.cu", "md2_tile.cuh", "md2_platform.h", "md2_host.h")]
-    srcs.append(os.path.join(ROOT, "include", "md2_loss.h"))
+    srcs = [os.path.join(CSRC, f) for f in ("md2_abi.cu", "md2_l1.cu", "md2_tile.cuh", "md2_platform.h", "md2_host.h")]
+    srcs += [os.path.join(ROOT, "include", h) for h in ("md2_loss.h", "md2_ops.h")]
     if not force and _newer(LIB, srcs):
         return LIB
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_verbose else []) + [srcs[0], "-o", LIB]
+    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_verbose else []) + srcs[:2] + ["-o", LIB]
     out = _run(cmd, verbose)
     if ptxas_verbose:
         print(out)
@@ -56,7 +56,7 @@ def build_cuda_library(force=False, verbose=False, ptxas_verbose=False):
 
 def build_torch_extension(force=False, verbose=False):
     src = os.path.join(CSRC, "torch_ext.cpp")
-    deps = [src, os.path.join(ROOT, "include", "md2_loss.h")]
+    deps = [src, os.path.join(ROOT, "include", "md2_loss.h"), os.path.join(ROOT, "include", "md2_ops.h")]
     if not force and _newer(EXT, deps) and os.path.exists(LIB):
         return EXT
     import torch

@@ -51,6 +51,28 @@ EXPORTS = ["md2_workspace_bytes", "md2_loss_forward", "md2_loss_forward_backward
            "md2_launches_per_step", "md2_version", "md2_debug_warp", "md2_set_tile_kernel_events",
            "md2_debug_div"]
 
+# include/md2_ops.h: the symbol-level operators (name -> argument types; all return int)
+_V, _I, _L, _D = C.c_void_p, C.c_int, C.c_longlong, C.c_double
+OPS_PROTOTYPES = {
+    "md2_disp2depth_forward": [_L, _V, _D, _D, _V, _V, _V],
+    "md2_disp2depth_backward": [_L, _V, _D, _D, _V, _V, _V, _V],
+    "md2_upsample_forward": [_I, _I, _I, _I, _I, _V, _V, _V],
+    "md2_upsample_backward": [_I, _I, _I, _I, _I, _V, _V, _V],
+    "md2_backproject_forward": [_I, _I, _I, _V, _V, _V, _V],
+    "md2_backproject_backward": [_I, _I, _I, _V, _V, _V, _V],
+    "md2_project_forward": [_I, _I, _I, _V, _V, _V, _D, _V, _V],
+    "md2_project_backward": [_I, _I, _I, _V, _V, _V, _D, _V, _V, _V, _V],
+    "md2_grid_sample_forward": [_I, _I, _I, _I, _I, _I, _V, _V, _V, _V],
+    "md2_grid_sample_backward": [_I, _I, _I, _I, _I, _I, _V, _V, _V, _V, _V],
+    "md2_reprojection_forward": [_I, _I, _I, _V, _V, _V, _V],
+    "md2_reprojection_backward": [_I, _I, _I, _V, _V, _V, _V, _V],
+    "md2_smooth_forward": [_I, _I, _I, _V, _V, _V, _V, _V],
+    "md2_smooth_backward": [_I, _I, _I, _V, _V, _V, _V, _V, _V],
+}
+EXPORTS += list(OPS_PROTOTYPES)
+
+MD2_ERR_NULL, MD2_ERR_SHAPE, MD2_ERR_CONFIG, MD2_ERR_WORKSPACE, MD2_ERR_NO_DEVICE = -1, -2, -3, -4, -5
+
 LIB_NAME = "libmd2loss.so"
 
 
@@ -95,6 +117,10 @@ def load_library(path=None):
     lib.md2_debug_warp.restype = C.c_int
     lib.md2_debug_warp.argtypes = [C.POINTER(md2_cfg), C.POINTER(md2_inputs), C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    for name, argtypes in OPS_PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
     return lib
 
 

@@ -1,0 +1,297 @@
+"""Symbol-level drop-ins (SURVEY.md 8b "L1"): the reference's unfused operators, same names and
+signatures, each backed by a kernel of csrc/md2_l1.cu through the C ABI of include/md2_ops.h.
+
+  model_layer/warp.py        grid_sample :12, interpolate :18, disparity2depth :29, param2matrix :126,
+                             Depth2PointCloud :193, PointCloud2Pixel :250
+  model_loss/model_loss.py   ReprojectionLoss :92, SmoothLoss :107
+
+The training path does not go through these (it uses functional.view_synthesis_loss, one fused kernel);
+they serve a caller that composes the operators itself.  Every forward reproduces the rounding sequence of
+the ATen operators the reference calls, every backward is an analytic kernel registered with autograd.
+fp32 CUDA tensors only; anything else raises (there is no PyTorch or CPU implementation behind them).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import cabi
+from .functional import param2matrix  # noqa: F401  (warp.py:126-153)
+
+_lib = None
+
+
+def _L():
+    global _lib
+    if _lib is None:
+        _lib = cabi.load_library()
+    return _lib
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32):
+        raise RuntimeError(f"{name}: expected a float32 CUDA tensor (got {getattr(t, 'dtype', type(t))} on "
+                           f"{getattr(t, 'device', '?')}); md2_b200 has no CPU or mixed-precision path")
+    return t.contiguous()
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed with code {rc}")
+
+
+# ----------------------------------------------------------------------------- disparity2depth
+class _Disp2Depth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, min_depth, max_depth):
+        disp = _f32(disp, "disparity2depth")
+        scaled, depth = torch.empty_like(disp), torch.empty_like(disp)
+        with torch.cuda.device(disp.device):
+            _check(_L().md2_disp2depth_forward(disp.numel(), _p(disp), min_depth, max_depth, _p(scaled), _p(depth),
+                                               _st()), "md2_disp2depth_forward")
+        ctx.save_for_backward(disp)
+        ctx.rng = (min_depth, max_depth)
+        return scaled, depth
+
+    @staticmethod
+    def backward(ctx, g_scaled, g_depth):
+        (disp,) = ctx.saved_tensors
+        g = torch.empty_like(disp)
+        gs = g_scaled.contiguous() if g_scaled is not None else None
+        gd = g_depth.contiguous() if g_depth is not None else None
+        with torch.cuda.device(disp.device):
+            _check(_L().md2_disp2depth_backward(disp.numel(), _p(disp), ctx.rng[0], ctx.rng[1], _p(gs), _p(gd), _p(g),
+                                                _st()), "md2_disp2depth_backward")
+        return g, None, None
+
+
+def disparity2depth(disparity, min_depth, max_depth):
+    """warp.py:29-39 -> (scaled_disp, depth)."""
+    return _Disp2Depth.apply(disparity, float(min_depth), float(max_depth))
+
+
+# ----------------------------------------------------------------------------- interpolate
+class _Upsample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        x = _f32(x, "interpolate")
+        N, Cc, h, w = x.shape
+        out = torch.empty(N, Cc, H, W, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _check(_L().md2_upsample_forward(N * Cc, h, w, H, W, _p(x), _p(out), _st()), "md2_upsample_forward")
+        ctx.shape = (N, Cc, h, w, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, Cc, h, w, H, W = ctx.shape
+        g = g.contiguous()
+        gi = torch.empty(N, Cc, h, w, device=g.device, dtype=torch.float32)
+        with torch.cuda.device(g.device):
+            _check(_L().md2_upsample_backward(N * Cc, h, w, H, W, _p(g), _p(gi), _st()), "md2_upsample_backward")
+        return gi, None, None
+
+
+def interpolate(tensor, height, width, mode, align_corners):
+    """warp.py:18-20; the reference only ever asks for ("bilinear", False) (processor.py:146)."""
+    if mode != "bilinear" or align_corners:
+        raise NotImplementedError("md2_b200.interpolate: only mode='bilinear', align_corners=False (processor.py:146)")
+    return _Upsample.apply(tensor, int(height), int(width))
+
+
+# ----------------------------------------------------------------------------- grid_sample
+class _GridSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, grid):
+        img, grid = _f32(img, "grid_sample"), _f32(grid, "grid_sample")
+        B, Cc, H, W = img.shape
+        if grid.dim() != 4 or grid.shape[0] != B or grid.shape[3] != 2:
+            raise RuntimeError(f"grid_sample: coords must be [B,Ho,Wo,2], got {tuple(grid.shape)}")
+        Ho, Wo = grid.shape[1], grid.shape[2]
+        out = torch.empty(B, Cc, Ho, Wo, device=img.device, dtype=torch.float32)
+        with torch.cuda.device(img.device):
+            _check(_L().md2_grid_sample_forward(B, Cc, H, W, Ho, Wo, _p(img), _p(grid), _p(out), _st()),
+                   "md2_grid_sample_forward")
+        ctx.save_for_backward(img, grid)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        img, grid = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("md2_b200.grid_sample: the sampled image is data on the reference's path "
+                                      "(processor.py:172-176); no gradient with respect to it")
+        B, Cc, H, W = img.shape
+        g = g.contiguous()
+        gg = torch.empty_like(grid)
+        with torch.cuda.device(img.device):
+            _check(_L().md2_grid_sample_backward(B, Cc, H, W, grid.shape[1], grid.shape[2], _p(img), _p(grid), _p(g),
+                                                 _p(gg), _st()), "md2_grid_sample_backward")
+        return None, gg
+
+
+def grid_sample(tensor, coords, padding_mode, align_corners):
+    """warp.py:12-14; the reference only ever asks for ("border", True) (processor.py:172-176)."""
+    if padding_mode != "border" or not align_corners:
+        raise NotImplementedError("md2_b200.grid_sample: only padding_mode='border', align_corners=True")
+    return _GridSample.apply(tensor, coords)
+
+
+# ----------------------------------------------------------------------------- Depth2PointCloud
+class _Backproject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, inv_K, B, H, W):
+        depth, inv_K = _f32(depth, "Depth2PointCloud"), _f32(inv_K, "Depth2PointCloud")
+        if depth.numel() != B * H * W or tuple(inv_K.shape) != (B, 4, 4):
+            raise RuntimeError(f"Depth2PointCloud: depth {tuple(depth.shape)} / inv_K {tuple(inv_K.shape)} do not "
+                               f"match batch {B}, {H}x{W}")
+        cam = torch.empty(B, 4, H * W, device=depth.device, dtype=torch.float32)
+        with torch.cuda.device(depth.device):
+            _check(_L().md2_backproject_forward(B, H, W, _p(depth), _p(inv_K), _p(cam), _st()), "md2_backproject_forward")
+        ctx.save_for_backward(inv_K)
+        ctx.dims = (B, H, W, depth.shape)
+        return cam
+
+    @staticmethod
+    def backward(ctx, g):
+        (inv_K,) = ctx.saved_tensors
+        B, H, W, shape = ctx.dims
+        g = g.contiguous()
+        gd = torch.empty(shape, device=g.device, dtype=torch.float32)
+        with torch.cuda.device(g.device):
+            _check(_L().md2_backproject_backward(B, H, W, _p(inv_K), _p(g), _p(gd), _st()), "md2_backproject_backward")
+        return gd, None, None, None, None
+
+
+class Depth2PointCloud(nn.Module):
+    """warp.py:193-246: depth [B,1,H,W], inv_K [B,4,4] -> homogeneous camera points [B,4,H*W].  The pixel grid
+    the reference keeps as a parameter is generated inside the kernel."""
+
+    def __init__(self, batch_size, height, width):
+        super().__init__()
+        self.batch_size, self.height, self.width = batch_size, height, width
+
+    def forward(self, depth, inverse_intrinsic_matrix):
+        return _Backproject.apply(depth, inverse_intrinsic_matrix, self.batch_size, self.height, self.width)
+
+
+# ----------------------------------------------------------------------------- PointCloud2Pixel
+class _Project(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cam, K, T, B, H, W, eps):
+        cam, K, T = _f32(cam, "PointCloud2Pixel"), _f32(K, "PointCloud2Pixel"), _f32(T, "PointCloud2Pixel")
+        if tuple(cam.shape) != (B, 4, H * W) or tuple(K.shape) != (B, 4, 4) or tuple(T.shape) != (B, 4, 4):
+            raise RuntimeError(f"PointCloud2Pixel: cam {tuple(cam.shape)}, K {tuple(K.shape)}, T {tuple(T.shape)} do "
+                               f"not match batch {B}, {H}x{W}")
+        grid = torch.empty(B, H, W, 2, device=cam.device, dtype=torch.float32)
+        with torch.cuda.device(cam.device):
+            _check(_L().md2_project_forward(B, H, W, _p(cam), _p(K), _p(T), eps, _p(grid), _st()), "md2_project_forward")
+        ctx.save_for_backward(cam, K, T)
+        ctx.dims = (B, H, W, eps)
+        return grid
+
+    @staticmethod
+    def backward(ctx, g):
+        cam, K, T = ctx.saved_tensors
+        B, H, W, eps = ctx.dims
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("md2_b200.PointCloud2Pixel: the intrinsics are data (processor.py:166-170)")
+        g = g.contiguous()
+        g_cam, g_T = torch.empty_like(cam), torch.empty_like(T)
+        with torch.cuda.device(cam.device):
+            _check(_L().md2_project_backward(B, H, W, _p(cam), _p(K), _p(T), eps, _p(g), _p(g_cam), _p(g_T), _st()),
+                   "md2_project_backward")
+        return g_cam, None, g_T, None, None, None, None
+
+
+class PointCloud2Pixel(nn.Module):
+    """warp.py:250-269: camera points [B,4,H*W], K, T [B,4,4] -> normalised sampling grid [B,H,W,2]."""
+
+    def __init__(self, batch_size, height, width, eps=1e-7):
+        super().__init__()
+        self.batch_size, self.height, self.width, self.eps = batch_size, height, width, eps
+
+    def forward(self, camera_coords, intrinsic_matrix, transformation_matrix):
+        return _Project.apply(camera_coords, intrinsic_matrix, transformation_matrix, self.batch_size, self.height,
+                              self.width, float(self.eps))
+
+
+# ----------------------------------------------------------------------------- ReprojectionLoss
+class _Reprojection(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred, target = _f32(pred, "ReprojectionLoss"), _f32(target, "ReprojectionLoss")
+        if pred.shape != target.shape or pred.dim() != 4 or pred.shape[1] != 3:
+            raise RuntimeError(f"ReprojectionLoss: expected two [B,3,H,W] tensors, got {tuple(pred.shape)} and "
+                               f"{tuple(target.shape)}")
+        B, _, H, W = pred.shape
+        out = torch.empty(B, 1, H, W, device=pred.device, dtype=torch.float32)
+        with torch.cuda.device(pred.device):
+            _check(_L().md2_reprojection_forward(B, H, W, _p(pred), _p(target), _p(out), _st()), "md2_reprojection_forward")
+        ctx.save_for_backward(pred, target)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("md2_b200.ReprojectionLoss: the target is data (processor.py:192-204)")
+        B, _, H, W = pred.shape
+        g = g.contiguous()
+        gp = torch.empty_like(pred)
+        with torch.cuda.device(pred.device):
+            _check(_L().md2_reprojection_backward(B, H, W, _p(pred), _p(target), _p(g), _p(gp), _st()),
+                   "md2_reprojection_backward")
+        return gp, None
+
+
+class ReprojectionLoss(nn.Module):
+    """model_loss.py:92-103: 0.85 * SSIM dissimilarity + 0.15 * L1, channel means -> [B,1,H,W]."""
+
+    def forward(self, prediction, target):
+        return _Reprojection.apply(prediction, target)
+
+
+# ----------------------------------------------------------------------------- SmoothLoss
+class _Smooth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, color):
+        disp, color = _f32(disp, "SmoothLoss"), _f32(color, "SmoothLoss")
+        B, c1, h, w = disp.shape
+        if c1 != 1 or tuple(color.shape) != (B, 3, h, w):
+            raise RuntimeError(f"SmoothLoss: expected disp [B,1,h,w] and color [B,3,h,w], got {tuple(disp.shape)} and "
+                               f"{tuple(color.shape)}")
+        loss = torch.empty(1, device=disp.device, dtype=torch.float32)
+        part = torch.empty(B * 3, device=disp.device, dtype=torch.float32)
+        with torch.cuda.device(disp.device):
+            _check(_L().md2_smooth_forward(B, h, w, _p(disp), _p(color), _p(loss), _p(part), _st()), "md2_smooth_forward")
+        ctx.save_for_backward(disp, color, part)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        disp, color, part = ctx.saved_tensors
+        B, _, h, w = disp.shape
+        g = g.reshape(1).contiguous()
+        gd = torch.empty_like(disp)
+        with torch.cuda.device(disp.device):
+            _check(_L().md2_smooth_backward(B, h, w, _p(disp), _p(color), _p(part), _p(g), _p(gd), _st()),
+                   "md2_smooth_backward")
+        return gd, None
+
+
+class SmoothLoss(nn.Module):
+    """model_loss.py:107-116: mean-normalised disparity, edge-aware first differences -> 0-dim loss."""
+
+    def forward(self, disp, color):
+        return _Smooth.apply(disp, color)

@@ -1,0 +1,96 @@
+"""Golden vectors for the symbol-level operators (SURVEY.md 8b "L1"), produced by the UNMODIFIED reference
+symbols of model_layer/warp.py and model_loss/model_loss.py on CPU fp32.
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden_ops.py
+Writes tests/golden/ops.npz: for every operator its inputs, its output, a fixed cotangent and the gradients
+autograd returns for that cotangent.
+"""
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("MD2_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+import torch  # noqa: E402
+
+for _m in ["matplotlib", "matplotlib.pyplot", "albumentations", "albumentations.pytorch",
+           "albumentations.pytorch.transforms", "albumentations.augmentations",
+           "albumentations.augmentations.transforms", "skimage", "skimage.transform"]:
+    sys.modules[_m] = MagicMock()
+sys.modules["albumentations"].__version__ = "0.5.2"
+
+from model_layer.warp import (Depth2PointCloud, PointCloud2Pixel, disparity2depth, grid_sample,  # noqa: E402
+                              interpolate)
+from model_loss.model_loss import ReprojectionLoss, SmoothLoss  # noqa: E402
+
+import md2_b200.synthetic as syn  # noqa: E402
+
+B, H, W = 2, 24, 32
+
+
+def main():
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(5)
+    rnd = lambda *s: torch.rand(*s, generator=g)
+    d = {}
+
+    disp_lo = rnd(B, 1, H // 2, W // 2).requires_grad_(True)
+    up = interpolate(disp_lo, H, W, "bilinear", False)
+    cot = torch.randn(up.shape, generator=g)
+    d.update(up_in=disp_lo, up_out=up, up_cot=cot, up_grad=torch.autograd.grad((up * cot).sum(), disp_lo)[0])
+
+    disp = rnd(B, 1, H, W).requires_grad_(True)
+    scaled, depth = disparity2depth(disp, 0.1, 100.0)
+    c0, c1 = torch.randn(scaled.shape, generator=g), torch.randn(depth.shape, generator=g) * 1e-2
+    d.update(d2d_in=disp, d2d_scaled=scaled, d2d_depth=depth, d2d_cot0=c0, d2d_cot1=c1,
+             d2d_grad=torch.autograd.grad((scaled * c0).sum() + (depth * c1).sum(), disp)[0])
+
+    K4, inv_K = syn.make_intrinsics(B, H, W, "monodepth2")
+    depth_in = (0.5 + 5 * rnd(B, 1, H, W)).requires_grad_(True)
+    cam = Depth2PointCloud(B, H, W)(depth_in, inv_K)
+    cot = torch.randn(cam.shape, generator=g)
+    d.update(bp_depth=depth_in, bp_invK=inv_K, bp_cam=cam, bp_cot=cot,
+             bp_grad=torch.autograd.grad((cam * cot).sum(), depth_in)[0])
+
+    T = torch.eye(4)[None].repeat(B, 1, 1)
+    T[:, :3, :3] += 0.02 * torch.randn(B, 3, 3, generator=g)
+    T[:, :3, 3] = 0.2 * torch.randn(B, 3, generator=g)
+    T.requires_grad_(True)
+    cam_in = cam.detach().clone().requires_grad_(True)
+    grid = PointCloud2Pixel(B, H, W)(cam_in, K4, T)
+    cot = torch.randn(grid.shape, generator=g)
+    gc, gT = torch.autograd.grad((grid * cot).sum(), [cam_in, T])
+    d.update(pj_cam=cam_in, pj_K=K4, pj_T=T, pj_grid=grid, pj_cot=cot, pj_grad_cam=gc, pj_grad_T=gT)
+
+    img = rnd(B, 3, H, W)
+    grid_in = (grid.detach() + 0.05 * torch.randn(grid.shape, generator=g)).requires_grad_(True)  # some out of range
+    out = grid_sample(img, grid_in, "border", True)
+    cot = torch.randn(out.shape, generator=g)
+    d.update(gs_img=img, gs_grid=grid_in, gs_out=out, gs_cot=cot,
+             gs_grad=torch.autograd.grad((out * cot).sum(), grid_in)[0])
+
+    pred = rnd(B, 3, H, W).requires_grad_(True)
+    tgt = (pred.detach() + 0.1 * torch.randn(B, 3, H, W, generator=g)).clamp(0, 1)
+    rep = ReprojectionLoss()(pred, tgt)
+    cot = torch.randn(rep.shape, generator=g)
+    d.update(rp_pred=pred, rp_target=tgt, rp_out=rep, rp_cot=cot,
+             rp_grad=torch.autograd.grad((rep * cot).sum(), pred)[0])
+
+    sdisp = rnd(B, 1, H, W).requires_grad_(True)
+    sm = SmoothLoss()(sdisp, img)
+    d.update(sm_disp=sdisp, sm_color=img, sm_out=sm, sm_grad=torch.autograd.grad(sm, sdisp)[0])
+
+    path = os.path.join(HERE, "ops.npz")
+    np.savez_compressed(path, **{k: v.detach().numpy() for k, v in d.items()})
+    print("ops.npz", os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -22,12 +22,29 @@ def lib():
 
 
 def test_library_exports_every_declared_symbol(lib):
-    header = open(os.path.join(ROOT, "include", "md2_loss.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include"))))
     declared = set(re.findall(r"\b(md2_[a-z_0-9]+)\s*\(", header))
     assert declared == set(cabi.EXPORTS), declared ^ set(cabi.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
     assert b"sm_100a" in lib.md2_version()
+
+
+def test_operator_entry_points_validate_without_gpu(lib):
+    """include/md2_ops.h: argument errors are reported before anything is launched."""
+    null = C.c_void_p(0)
+    one = C.c_void_p(8)  # never dereferenced: the shape check comes first
+    assert lib.md2_disp2depth_forward(0, one, 0.1, 100.0, one, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_disp2depth_forward(4, one, 0.0, 100.0, one, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_disp2depth_forward(4, null, 0.1, 100.0, one, one, null) == cabi.MD2_ERR_NULL
+    assert lib.md2_upsample_forward(1, 0, 4, 8, 8, one, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_upsample_backward(1, 4, 4, 8, 8, null, one, null) == cabi.MD2_ERR_NULL
+    assert lib.md2_backproject_forward(0, 8, 8, one, one, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_project_forward(1, 1, 8, one, one, one, 1e-7, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_project_backward(1, 8, 8, one, one, one, 1e-7, one, one, null, null) == cabi.MD2_ERR_NULL
+    assert lib.md2_grid_sample_forward(1, 0, 8, 8, 8, 8, one, one, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_reprojection_forward(1, 2, 8, one, one, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_smooth_forward(1, 8, 8, one, one, null, one, null) == cabi.MD2_ERR_NULL
 
 
 def test_workspace_and_validation_without_gpu(lib):
