@@ -68,6 +68,8 @@ OPS_PROTOTYPES = {
     "md2_reprojection_backward": [_I, _I, _I, _V, _V, _V, _V, _V],
     "md2_smooth_forward": [_I, _I, _I, _V, _V, _V, _V, _V],
     "md2_smooth_backward": [_I, _I, _I, _V, _V, _V, _V, _V, _V],
+    "md2_mean_inv_depth_forward": [_I, _I, _V, _V, _V],
+    "md2_mean_inv_depth_backward": [_I, _I, _V, _V, _V, _V],
 }
 EXPORTS += list(OPS_PROTOTYPES)
 

@@ -6,6 +6,12 @@ Mirrors compute.image2warping / compute.compute_loss of
 path as one fused CUDA pass.  image2warping launches it (all its inputs exist by then) and
 leaves outputs[("depth", 0, s)] and the loss; compute_loss publishes outputs["loss"].
 ``("warp_color", f, s)`` is never materialised (its only consumer was compute_loss).
+
+``pose_type == "posecnn"`` (processor.py:153-157) makes the pose of every scale a function of that
+scale's depth map, which the fused kernel (one pose per source) does not cover.  That branch is
+composed from the symbol-level kernels of modules.py instead: the operators are
+this package's CUDA kernels, the cat / min / mean glue between them is the reference's own torch code,
+and ``("warp_color", f, s)`` is materialised as in the reference.
 """
 from __future__ import annotations
 
@@ -20,15 +26,55 @@ class compute(object):
         self.device = device
         self.step = 0
 
-    def _check_supported(self):
-        if getattr(self.opt, "pose_type", "separate") == "posecnn":
-            # processor.py:153-157 rescales the translation by mean(1/depth) per scale, i.e. T depends
-            # on the depth map; that variant is outside the fused path
-            raise NotImplementedError("pose_type='posecnn' is not supported by the fused loss; "
-                                      "use pose_type 'separate' or 'shared'")
+    def _posecnn(self):
+        return getattr(self.opt, "pose_type", "separate") == "posecnn"
+
+    # ---- posecnn: composed from the symbol-level kernels (processor.py:139-163 with the :153-157 branch)
+    def _image2warping_composed(self, inputs, outputs):
+        from . import modules as M
+        opt = self.opt
+        B = inputs[("color", 0, 0)].shape[0]
+        H, W = opt.height, opt.width
+        backproject, project = M.Depth2PointCloud(B, H, W), M.PointCloud2Pixel(B, H, W)
+        for s in opt.scales:
+            disp = M.interpolate(outputs[("disp", s)], H, W, "bilinear", False)
+            _, depth = M.disparity2depth(disp, opt.min_depth, opt.max_depth)
+            outputs[("depth", 0, s)] = depth
+            cam = backproject(depth, inputs[("inv_K", 0)])
+            for f in opt.frame_ids[1:]:
+                if f == "s":
+                    T = inputs["stereo"]
+                    T = T if T.dim() == 3 else T[None].expand(B, 4, 4)
+                else:
+                    aa, tr = outputs[("R", f, 0)], outputs[("T", f, 0)]
+                    T = F_.param2matrix(aa[:, 0], tr[:, 0] * M.mean_inv_depth(depth)[:, 0], invert=(f < 0))
+                grid = project(cam, inputs[("K", 0)], T.contiguous())
+                outputs[("warp_color", f, s)] = M.grid_sample(inputs[("color", f, 0)], grid, "border", True)
+        return inputs, outputs
+
+    def _compute_loss_composed(self, inputs, outputs, noise=None):
+        from . import modules as M
+        opt = self.opt
+        reprojection, smooth = M.ReprojectionLoss(), M.SmoothLoss()
+        target = inputs[("color", 0, 0)]
+        srcs = list(opt.frame_ids[1:])
+        total = 0
+        for i, s in enumerate(opt.scales):
+            rep = torch.cat([reprojection(outputs[("warp_color", f, s)], target) for f in srcs], 1)
+            if opt.use_automasking:
+                ident = torch.cat([reprojection(inputs[("color", f, 0)], target) for f in srcs], 1)
+                draw = noise[i] if noise is not None else torch.randn(ident.shape, device=ident.device)
+                rep = torch.cat((ident + 0.00001 * draw, rep), dim=1)
+            to_optimise = rep if rep.shape[1] == 1 else torch.min(rep, dim=1)[0]
+            total = total + to_optimise.mean() + \
+                opt.disp_smoothness * smooth(outputs[("disp", s)], inputs[("color", 0, s)]) / (2 ** s)
+        outputs["loss"] = total / len(opt.scales)
+        return outputs
 
     def image2warping(self, inputs, outputs, setting=None, noise=None):
-        self._check_supported()
+        if self._posecnn():
+            self._noise = noise
+            return self._image2warping_composed(inputs, outputs)
         opt = self.opt
         scales = list(opt.scales)
         srcs = list(opt.frame_ids[1:])
@@ -49,6 +95,8 @@ class compute(object):
         return inputs, outputs
 
     def compute_loss(self, inputs, outputs, setting=None):
+        if self._posecnn():
+            return self._compute_loss_composed(inputs, outputs, getattr(self, "_noise", None))
         if ("fused_loss",) not in outputs:
             self.image2warping(inputs, outputs, setting)
         outputs["loss"] = outputs.pop(("fused_loss",))

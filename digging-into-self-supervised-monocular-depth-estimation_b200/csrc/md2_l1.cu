@@ -410,6 +410,28 @@ __global__ void __launch_bounds__(256) smooth_l1_bwd(int B, int h, int w, const 
   }
 }
 
+// --------------------------------------------------------------------------- mean(1 / depth) per image (processor.py:155)
+__global__ void __launch_bounds__(256) mean_inv_fwd(int n, const float* __restrict__ depth, float* out) {
+  __shared__ float red[8];
+  const float* d = depth + (long long)blockIdx.x * n;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) acc += __frcp_rn(d[i]);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int wv = 0; wv < 8; ++wv) a += red[wv];
+    out[blockIdx.x] = a / (float)n;
+  }
+}
+__global__ void mean_inv_bwd(int B, int n, const float* __restrict__ depth, const float* __restrict__ g, float* g_depth) {
+  MD2_GRID_STRIDE(i, (long long)B * n) {
+    const float d = depth[i];
+    g_depth[i] = -g[i / n] / ((float)n * d * d);
+  }
+}
+
 static inline int rc(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 
 }  // namespace md2
@@ -523,6 +545,19 @@ int md2_smooth_backward(int B, int h, int w, const float* disp, const float* col
   if (B <= 0 || h <= 0 || w <= 0) return MD2_ERR_SHAPE;
   if (!disp || !color || !part || !g_loss_dev || !g_disp) return MD2_ERR_NULL;
   smooth_l1_bwd<<<blocks_for((long long)B * h * w), 256, 0, (cudaStream_t)st>>>(B, h, w, disp, color, part, g_loss_dev, g_disp);
+  return rc(cudaGetLastError());
+}
+
+int md2_mean_inv_depth_forward(int B, int n, const float* depth, float* out, md2_stream_t st) {
+  if (B <= 0 || n <= 0) return MD2_ERR_SHAPE;
+  if (!depth || !out) return MD2_ERR_NULL;
+  mean_inv_fwd<<<B, 256, 0, (cudaStream_t)st>>>(n, depth, out);
+  return rc(cudaGetLastError());
+}
+int md2_mean_inv_depth_backward(int B, int n, const float* depth, const float* g_out, float* g_depth, md2_stream_t st) {
+  if (B <= 0 || n <= 0) return MD2_ERR_SHAPE;
+  if (!depth || !g_out || !g_depth) return MD2_ERR_NULL;
+  mean_inv_bwd<<<blocks_for((long long)B * n), 256, 0, (cudaStream_t)st>>>(B, n, depth, g_out, g_depth);
   return rc(cudaGetLastError());
 }
 

@@ -295,3 +295,33 @@ class SmoothLoss(nn.Module):
 
     def forward(self, disp, color):
         return _Smooth.apply(disp, color)
+
+
+# ----------------------------------------------------------------------------- mean inverse depth (posecnn)
+class _MeanInvDepth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth):
+        depth = _f32(depth, "mean_inv_depth")
+        B = depth.shape[0]
+        out = torch.empty(B, device=depth.device, dtype=torch.float32)
+        with torch.cuda.device(depth.device):
+            _check(_L().md2_mean_inv_depth_forward(B, depth.numel() // B, _p(depth), _p(out), _st()),
+                   "md2_mean_inv_depth_forward")
+        ctx.save_for_backward(depth)
+        return out.view(B, 1, 1, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        (depth,) = ctx.saved_tensors
+        B = depth.shape[0]
+        g = g.reshape(B).contiguous()
+        gd = torch.empty_like(depth)
+        with torch.cuda.device(depth.device):
+            _check(_L().md2_mean_inv_depth_backward(B, depth.numel() // B, _p(depth), _p(g), _p(gd), _st()),
+                   "md2_mean_inv_depth_backward")
+        return gd
+
+
+def mean_inv_depth(depth):
+    """(1 / depth).mean(3, True).mean(2, True) of processor.py:155 -> [B,1,1,1]."""
+    return _MeanInvDepth.apply(depth)

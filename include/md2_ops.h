@@ -1,8 +1,8 @@
 /* md2_ops.h - C ABI of the reference's symbol-level (unfused) operators, SURVEY.md 8b "L1".
  *
  * The training path is the fused kernel of md2_loss.h.  These entry points cover a caller that composes
- * the operators itself (model_tool/processor.py:139-187 does, and its posecnn branch :153-157 multiplies
- * the camera points by a per-pixel pose in between).  Same conventions as md2_loss.h: device pointers to
+ * the operators itself (model_tool/processor.py:139-187 does, and its posecnn branch :153-157 derives a
+ * per-scale pose from the depth map in between).  Same conventions as md2_loss.h: device pointers to
  * contiguous fp32 NCHW, the caller's stream, return 0 / MD2_ERR_* (<0) / cudaError_t (>0), no torch types,
  * no CPU path.  Each forward reproduces the rounding sequence of the ATen operators the reference calls;
  * each backward is the analytic adjoint (gradients overwrite their output buffer).
@@ -66,6 +66,12 @@ int md2_smooth_forward(int B, int h, int w, const float* disp, const float* colo
                        md2_stream_t stream);
 int md2_smooth_backward(int B, int h, int w, const float* disp, const float* color, const float* part,
                         const float* g_loss_dev, float* g_disp, md2_stream_t stream);
+
+/* (1 / depth).mean(3, True).mean(2, True) of the posecnn branch (model_tool/processor.py:155):
+ * depth [B, n = H*W] -> out [B]; the backward returns dL/d depth from g_out [B]. */
+int md2_mean_inv_depth_forward(int B, int n, const float* depth, float* out, md2_stream_t stream);
+int md2_mean_inv_depth_backward(int B, int n, const float* depth, const float* g_out, float* g_depth,
+                                md2_stream_t stream);
 
 #ifdef __cplusplus
 }

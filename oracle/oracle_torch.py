@@ -150,7 +150,7 @@ def smoothness(disp, color):
 
 def view_synthesis_loss(target, sources, disps, color_pyr, K, inv_K, Ts, *,
                         min_depth=0.1, max_depth=100.0, disp_smoothness=1e-3,
-                        automask=True, noise=None, taps=False):
+                        automask=True, noise=None, taps=False, posecnn=None):
     """model_tool/processor.py:139-218 (image2warping followed by compute_loss) for
     one batch, as a function of explicit tensors.
 
@@ -159,7 +159,10 @@ def view_synthesis_loss(target, sources, disps, color_pyr, K, inv_K, Ts, *,
     noise: per-scale [B,S,H,W] standard-normal draws, or None to draw them the way
     the reference does (host torch.randn per scale, processor.py:195).
     Returns a dict: loss (0-dim), depth[s], per_pixel[s] [B,H,W], argmin[s] [B,H,W]
-    (+ warped / grid / rep / ident taps when ``taps``)."""
+    (+ warped / grid / rep / ident taps when ``taps``).
+    posecnn: None, or per source (axisangle [B,1,3], translation [B,1,3], invert): the pose_type
+    "posecnn" branch (processor.py:153-157), where the pose of each scale is built from the
+    translation scaled by that scale's mean inverse depth (``Ts`` is then ignored)."""
     B, _, H, W = target.shape
     S = len(sources)
     pix = pixel_rays_grid(B, H, W, target.dtype, target.device)
@@ -173,7 +176,13 @@ def view_synthesis_loss(target, sources, disps, color_pyr, K, inv_K, Ts, *,
         reps, warps, grids = [], [], []
         for f in range(S):
             cam = backproject(depth, inv_K, pix)
-            grid = project(cam, K, Ts[f], H, W)
+            if posecnn is not None:
+                aa, tr, inv = posecnn[f]
+                mean_inv_depth = (1 / depth).mean(3, True).mean(2, True)
+                T = pose_matrix(aa, tr * mean_inv_depth[:, 0], invert=inv)
+            else:
+                T = Ts[f]
+            grid = project(cam, K, T, H, W)
             w = sample_border(sources[f], grid)
             reps.append(photometric_error(w, target))
             if taps:

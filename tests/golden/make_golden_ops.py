@@ -29,6 +29,7 @@ sys.modules["albumentations"].__version__ = "0.5.2"
 from model_layer.warp import (Depth2PointCloud, PointCloud2Pixel, disparity2depth, grid_sample,  # noqa: E402
                               interpolate)
 from model_loss.model_loss import ReprojectionLoss, SmoothLoss  # noqa: E402
+from model_tool.processor import compute  # noqa: E402
 
 import md2_b200.synthetic as syn  # noqa: E402
 
@@ -92,5 +93,50 @@ def main():
     print("ops.npz", os.path.getsize(path) // 1024, "KiB")
 
 
+def posecnn_case(seed=9, Bp=2, Hp=32, Wp=64):
+    """The reference's compute.image2warping + compute_loss with pose_type='posecnn' (processor.py:153-157)."""
+    from types import SimpleNamespace
+    torch.manual_seed(seed)
+    frame_ids = [0, -1, 1]
+    inputs, outputs = syn.make_batch(Bp, Hp, Wp, frame_ids, 4, seed, "smooth", "monodepth2")
+    for f in frame_ids[1:]:
+        outputs[("R", f, 0)] = outputs.pop(("axisangle", f)).detach()[:, None].clone().requires_grad_(True)
+        outputs[("T", f, 0)] = outputs.pop(("translation", f)).detach()[:, None].clone().requires_grad_(True)
+    opt = SimpleNamespace(frame_ids=frame_ids, scales=range(4), height=Hp, width=Wp, min_depth=0.1, max_depth=100.0,
+                          pose_type="posecnn", pose_frames=2, use_automasking=True, disp_smoothness=1e-3, batch=Bp)
+    setting = SimpleNamespace(inv_projection={0: Depth2PointCloud(Bp, Hp, Wp)},
+                              for_projection={0: PointCloud2Pixel(Bp, Hp, Wp)},
+                              loss={"reprojection": ReprojectionLoss(), "edge_aware": SmoothLoss()})
+    c = compute(opt, "cpu")
+    noise, orig = [], torch.randn
+
+    def rec(*a, **k):
+        r = orig(*a, **k)
+        noise.append(r.clone())
+        return r
+
+    torch.randn = rec
+    try:
+        c.image2warping(inputs, outputs, setting)
+        c.compute_loss(inputs, outputs, setting)
+    finally:
+        torch.randn = orig
+    outputs["loss"].backward()
+    d = {"loss": outputs["loss"].detach(), "K": inputs[("K", 0)], "inv_K": inputs[("inv_K", 0)]}
+    for f in frame_ids:
+        d[f"color{f}"] = inputs[("color", f, 0)]
+    for f in frame_ids[1:]:
+        d[f"R{f}"], d[f"T{f}"] = outputs[("R", f, 0)], outputs[("T", f, 0)]
+        d[f"grad_R{f}"], d[f"grad_T{f}"] = outputs[("R", f, 0)].grad, outputs[("T", f, 0)].grad
+    for s in range(4):
+        d[f"disp{s}"], d[f"grad_disp{s}"] = outputs[("disp", s)], outputs[("disp", s)].grad
+        d[f"color_pyr{s}"], d[f"noise{s}"] = inputs[("color", 0, s)], noise[s]
+        d[f"warp{s}"] = outputs[("warp_color", 1, s)]
+    path = os.path.join(HERE, "posecnn.npz")
+    np.savez_compressed(path, **{k: v.detach().numpy() for k, v in d.items()})
+    print("posecnn.npz", os.path.getsize(path) // 1024, "KiB, loss", float(d["loss"]))
+
+
 if __name__ == "__main__":
     main()
+    posecnn_case()

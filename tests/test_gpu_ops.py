@@ -224,3 +224,56 @@ def test_composed_operators_equal_fused_loss(M):
         _close(a, b, 2e-4)
     for a, b in zip(grads[4:], fused[4:]):
         _close(a, b, 2e-3)
+
+
+def test_mean_inv_depth(M):
+    g = torch.Generator(device=DEV).manual_seed(6)
+    depth = 0.2 + 20 * _rand(g, 3, 1, 96, 160)
+    d1, d2 = depth.clone().requires_grad_(True), depth.clone().requires_grad_(True)
+    out = M.mean_inv_depth(d1)
+    ref = (1 / d2).mean(3, True).mean(2, True)
+    assert out.shape == ref.shape
+    _close(out, ref, 1e-6)
+    cot = torch.randn(ref.shape, generator=g, device=DEV)
+    _close(torch.autograd.grad((out * cot).sum(), d1)[0], torch.autograd.grad((ref * cot).sum(), d2)[0], 1e-5)
+
+
+def test_compute_posecnn_branch(M):
+    """pose_type='posecnn' (processor.py:153-157) through the drop-in object, against the reference's own run
+    (tests/golden/posecnn.npz) and the oracle on the GPU."""
+    from types import SimpleNamespace
+    from md2_b200.compute import compute
+    from test_oracle_ops_golden import _load, posecnn_args
+    z = _load("posecnn.npz")
+    a = posecnn_args(z, DEV)
+    B, _, H, W = a["target"].shape
+    opt = SimpleNamespace(frame_ids=[0, -1, 1], scales=range(4), height=H, width=W, min_depth=0.1, max_depth=100.0,
+                          pose_type="posecnn", use_automasking=True, disp_smoothness=1e-3)
+    inputs = {("color", 0, 0): a["target"], ("color", -1, 0): a["sources"][0], ("color", 1, 0): a["sources"][1],
+              ("K", 0): a["K"], ("inv_K", 0): a["inv_K"]}
+    outputs = {}
+    for s in range(4):
+        inputs[("color", 0, s)] = a["color_pyr"][s]
+        outputs[("disp", s)] = a["disps"][s]
+    for f in (-1, 1):
+        outputs[("R", f, 0)], outputs[("T", f, 0)] = a["R"][f], a["T"][f]
+    c = compute(opt, torch.device(DEV))
+    c.image2warping(inputs, outputs, None, noise=a["noise"])
+    c.compute_loss(inputs, outputs, None)
+    wrt = a["disps"] + [a["R"][-1], a["R"][1], a["T"][-1], a["T"][1]]
+    grads = torch.autograd.grad(outputs["loss"], wrt)
+    ref_loss = float(z["loss"])
+    assert abs(float(outputs["loss"].detach()) - ref_loss) <= 1e-5 * abs(ref_loss)
+    for s in range(4):
+        _close(outputs[("warp_color", 1, s)], z[f"warp{s}"].to(DEV), 1e-4)
+        _close(grads[s], z[f"grad_disp{s}"].to(DEV), 1e-3)
+    for g_, k in zip(grads[4:], ["grad_R-1", "grad_R1", "grad_T-1", "grad_T1"]):
+        _close(g_, z[k].to(DEV), 2e-3)
+    # and the oracle evaluated by ATen on this GPU: same loss to fp32 rounding of the reductions
+    b = posecnn_args(z, DEV)
+    ref = O.view_synthesis_loss(b["target"], b["sources"], b["disps"], b["color_pyr"], b["K"], b["inv_K"], None,
+                                noise=b["noise"], posecnn=[(b["R"][f][:, 0], b["T"][f][:, 0], f < 0) for f in (-1, 1)])
+    assert abs(float(outputs["loss"].detach()) - float(ref["loss"].detach())) <= 2e-6 * abs(ref_loss)
+    rg = torch.autograd.grad(ref["loss"], b["disps"] + [b["R"][-1], b["R"][1], b["T"][-1], b["T"][1]])
+    for x, y in zip(grads, rg):
+        _close(x, y, 1e-3)

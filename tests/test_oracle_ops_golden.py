@@ -9,8 +9,8 @@ from oracle import oracle_torch as O
 from helpers import GOLDEN_DIR
 
 
-def _load():
-    z = np.load(os.path.join(GOLDEN_DIR, "ops.npz"))
+def _load(name="ops.npz"):
+    z = np.load(os.path.join(GOLDEN_DIR, name))
     return {k: torch.from_numpy(z[k]) for k in z.files}
 
 
@@ -66,3 +66,32 @@ def test_reprojection_and_smoothness():
     sm = O.smoothness(d, z["sm_color"])
     _eq(sm, z["sm_out"])
     _eq(torch.autograd.grad(sm, d)[0], z["sm_grad"], 1e-6)
+
+
+def posecnn_args(z, device="cpu"):
+    t = lambda k: z[k].to(device)
+    leaf = lambda k: z[k].to(device).clone().requires_grad_(True)
+    disps = [leaf(f"disp{s}") for s in range(4)]
+    R = {f: leaf(f"R{f}") for f in (-1, 1)}
+    T = {f: leaf(f"T{f}") for f in (-1, 1)}
+    return dict(target=t("color0"), sources=[t("color-1"), t("color1")], disps=disps,
+                color_pyr=[t(f"color_pyr{s}") for s in range(4)], K=t("K"), inv_K=t("inv_K"),
+                noise=[t(f"noise{s}") for s in range(4)], R=R, T=T)
+
+
+def test_posecnn_branch():
+    """processor.py:153-157 (pose rebuilt per scale from the mean inverse depth) against the reference's run."""
+    z = _load("posecnn.npz")
+    a = posecnn_args(z)
+    out = O.view_synthesis_loss(a["target"], a["sources"], a["disps"], a["color_pyr"], a["K"], a["inv_K"], None,
+                                noise=a["noise"], taps=True,
+                                posecnn=[(a["R"][f][:, 0], a["T"][f][:, 0], f < 0) for f in (-1, 1)])
+    _eq(out["loss"], z["loss"])
+    for s in range(4):
+        _eq(out["warped"][s][1], z[f"warp{s}"])
+    wrt = a["disps"] + [a["R"][-1], a["R"][1], a["T"][-1], a["T"][1]]
+    grads = torch.autograd.grad(out["loss"], wrt)
+    for s in range(4):
+        _eq(grads[s], z[f"grad_disp{s}"], 1e-6)
+    for g, k in zip(grads[4:], ["grad_R-1", "grad_R1", "grad_T-1", "grad_T1"]):
+        _eq(g, z[k], 1e-5)
