@@ -71,7 +71,14 @@ OPS_PROTOTYPES = {
     "md2_mean_inv_depth_forward": [_I, _I, _V, _V, _V],
     "md2_mean_inv_depth_backward": [_I, _I, _V, _V, _V, _V],
 }
-EXPORTS += list(OPS_PROTOTYPES)
+EXPORTS += list(OPS_PROTOTYPES) + ["md2_metrics_workspace_bytes", "md2_depth_metrics"]
+
+
+class md2_metrics_cfg(C.Structure):
+    """include/md2_metrics.h"""
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Hg", C.c_int), ("Wg", C.c_int),
+                ("y0", C.c_int), ("y1", C.c_int), ("x0", C.c_int), ("x1", C.c_int),
+                ("min_depth", C.c_float), ("max_depth", C.c_float)]
 
 MD2_ERR_NULL, MD2_ERR_SHAPE, MD2_ERR_CONFIG, MD2_ERR_WORKSPACE, MD2_ERR_NO_DEVICE = -1, -2, -3, -4, -5
 
@@ -119,6 +126,11 @@ def load_library(path=None):
     lib.md2_debug_warp.restype = C.c_int
     lib.md2_debug_warp.argtypes = [C.POINTER(md2_cfg), C.POINTER(md2_inputs), C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.md2_metrics_workspace_bytes.restype = C.c_size_t
+    lib.md2_metrics_workspace_bytes.argtypes = [C.POINTER(md2_metrics_cfg)]
+    lib.md2_depth_metrics.restype = C.c_int
+    lib.md2_depth_metrics.argtypes = [C.POINTER(md2_metrics_cfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
     for name, argtypes in OPS_PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

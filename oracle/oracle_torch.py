@@ -229,3 +229,28 @@ def loss_and_grads(target, sources, disps, color_pyr, K, inv_K, Ts, grad_T_mask=
     it = iter(grads[len(disps):])
     out["grad_T"] = [next(it) if T.requires_grad else None for T in Ts]
     return out
+
+
+def depth_metrics(depth, gt, crop=(153, 371, 44, 1197)):
+    """model_loss/model_metric.py:70-106 (compute_depth_metric) with :43-63 (compute_depth_error,
+    lib="torch"): up-sample the prediction to the ground-truth size, clamp, mask gt > 0 inside the crop,
+    median scaling, clamp, then (abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3)."""
+    pred = torch.clamp(F.interpolate(depth, list(gt.shape[2:]), mode="bilinear", align_corners=False), 1e-3, 80)
+    pred = pred.detach()
+    mask = gt > 0
+    crop_mask = torch.zeros_like(mask)
+    crop_mask[:, :, crop[0]:crop[1], crop[2]:crop[3]] = 1
+    mask = mask * crop_mask
+    g = gt[mask]
+    p = pred[mask]
+    p = p * (torch.median(g) / torch.median(p))
+    p = torch.clamp(p, min=1e-3, max=80)
+    thr = torch.maximum(g / p, p / g)
+    a1 = (thr < 1.25).float().mean()
+    a2 = (thr < 1.25 ** 2).float().mean()
+    a3 = (thr < 1.25 ** 3).float().mean()
+    rmse = torch.sqrt(((g - p) ** 2).mean())
+    rmse_log = torch.sqrt(((torch.log(g) - torch.log(p)) ** 2).mean())
+    abs_rel = torch.mean(torch.abs(g - p) / g)
+    sq_rel = torch.mean((g - p) ** 2 / g)
+    return abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3

@@ -22,7 +22,7 @@ import torch  # noqa: E402
 
 for _m in ["matplotlib", "matplotlib.pyplot", "albumentations", "albumentations.pytorch",
            "albumentations.pytorch.transforms", "albumentations.augmentations",
-           "albumentations.augmentations.transforms", "skimage", "skimage.transform"]:
+           "albumentations.augmentations.transforms", "skimage", "skimage.transform", "cv2"]:
     sys.modules[_m] = MagicMock()
 sys.modules["albumentations"].__version__ = "0.5.2"
 
@@ -137,6 +137,25 @@ def posecnn_case(seed=9, Bp=2, Hp=32, Wp=64):
     print("posecnn.npz", os.path.getsize(path) // 1024, "KiB, loss", float(d["loss"]))
 
 
+def metrics_case(seed=13, Bm=2, Hm=48, Wm=160):
+    """compute_depth_metric (model_loss/model_metric.py:70-106) on a LiDAR-like sparse ground truth."""
+    from model_loss.model_metric import compute_depth_metric
+    g = torch.Generator().manual_seed(seed)
+    depth = 1.0 + 40 * torch.rand(Bm, 1, Hm, Wm, generator=g)
+    depth[0, 0, :4, :4] = 200.0       # clamped to 80
+    depth[1, 0, -4:, -4:] = 1e-5      # clamped to 1e-3
+    gt = torch.zeros(Bm, 1, 375, 1242)
+    hit = torch.rand(Bm, 1, 375, 1242, generator=g) < 0.02
+    gt[hit] = (2.0 + 60 * torch.rand(int(hit.sum()), generator=g))
+    m = compute_depth_metric({("depth", 0): gt}, {("depth", 0, 0): depth}, "torch")
+    path = os.path.join(HERE, "metrics.npz")
+    np.savez_compressed(path, depth=depth.numpy(), gt_idx=hit.flatten().nonzero()[:, 0].numpy().astype(np.int32),
+                        gt_val=gt[hit].numpy(), metrics=np.array([float(v) for v in m], dtype=np.float64),
+                        n=np.int64(int((hit[:, :, 153:371, 44:1197]).sum())))
+    print("metrics.npz", os.path.getsize(path) // 1024, "KiB", [round(float(v), 5) for v in m])
+
+
 if __name__ == "__main__":
     main()
     posecnn_case()
+    metrics_case()

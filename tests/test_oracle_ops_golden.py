@@ -95,3 +95,18 @@ def test_posecnn_branch():
         _eq(grads[s], z[f"grad_disp{s}"], 1e-6)
     for g, k in zip(grads[4:], ["grad_R-1", "grad_R1", "grad_T-1", "grad_T1"]):
         _eq(g, z[k], 1e-5)
+
+
+def metrics_golden(device="cpu"):
+    z = np.load(os.path.join(GOLDEN_DIR, "metrics.npz"))
+    depth = torch.from_numpy(z["depth"])
+    gt = torch.zeros(depth.shape[0] * 375 * 1242)
+    gt[torch.from_numpy(z["gt_idx"]).long()] = torch.from_numpy(z["gt_val"])
+    return depth.to(device), gt.view(depth.shape[0], 1, 375, 1242).to(device), z["metrics"], int(z["n"])
+
+
+def test_depth_metrics():
+    depth, gt, ref, _ = metrics_golden()
+    got = O.depth_metrics(depth, gt)
+    for a, b in zip(got, ref):
+        assert float(a) == float(np.float32(b)) or abs(float(a) - b) <= 1e-7 * abs(b), (float(a), b)
