@@ -120,13 +120,25 @@ def synthetic_batch(B, H, W, frame_ids, seed, device):
     return inputs
 
 
-def make_step(loss_impl, B, H, W, frame_ids, device, ddp):
-    """Returns (step_fn, images_per_step).  loss_impl: 'fused' (md2_b200) or 'eager' (PyTorch ops)."""
+def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_last=False):
+    """Returns (step_fn, images_per_step).  loss_impl: 'fused' (md2_b200) or 'eager' (PyTorch ops).
+    graph: capture forward + loss + backward + Adam in one CUDA graph (SURVEY.md 8f N3) and replay it per step;
+    the batch is copied into static input buffers on the device before every replay."""
     from types import SimpleNamespace
     nets = MonoNets().to(device)
+    if channels_last:   # NHWC activations for the cuDNN convolutions (precision-neutral); the loss inputs stay NCHW
+        nets = nets.to(memory_format=torch.channels_last)
+    if ddp and graph:
+        # tried in round 1 (DDP built and warmed up on a side stream, 11 eager iterations, then capture): the
+        # capture never completed on this stack (torch 2.11 / NCCL 2.28.9, 2 GPUs) - single-GPU only for now
+        raise NotImplementedError("--graph is single-GPU only: capturing the DDP step hung in round 1")
     model = nn.parallel.DistributedDataParallel(nets, device_ids=[device.index]) if ddp else nets
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graph)
     batches = [synthetic_batch(B, H, W, frame_ids, s, device) for s in range(2)]
+    if channels_last:
+        for b in batches:
+            for f in frame_ids:
+                b[("color_aug", f, 0)] = b[("color", f, 0)].contiguous(memory_format=torch.channels_last)
     cfg = SimpleNamespace(frame_ids=frame_ids, scales=range(4), height=H, width=W, min_depth=0.1, max_depth=100.0,
                           pose_type="separate", use_automasking=True, disp_smoothness=1e-3)
     if loss_impl == "fused":
@@ -138,7 +150,10 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp):
             for f in frame_ids[1:]:
                 outputs[("c2c", f, 0)] = F_.param2matrix(outputs[("axisangle", f)],
                                                          outputs[("translation", f)], invert=(f < 0))
-            comp.image2warping(inputs, outputs, None)
+            # under capture the seed would be frozen into the graph: draw the auto-mask noise with torch's
+            # graph-safe generator instead (what the reference does, processor.py:195)
+            noise = [torch.randn(B, len(frame_ids) - 1, H, W, device=device) for _ in range(4)] if graph else None
+            comp.image2warping(inputs, outputs, None, noise=noise)
             return comp.compute_loss(inputs, outputs, None)["loss"]
     else:
         from oracle import oracle_torch as O  # eager PyTorch restatement of the reference loss (baseline leg)
@@ -149,7 +164,9 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp):
             return O.view_synthesis_loss(inputs[("color", 0, 0)], [inputs[("color", f, 0)] for f in frame_ids[1:]],
                                          [outputs[("disp", s)] for s in range(4)],
                                          [inputs[("color", 0, s)] for s in range(4)], inputs[("K", 0)],
-                                         inputs[("inv_K", 0)], Ts)["loss"]
+                                         inputs[("inv_K", 0)], Ts,
+                                         noise=[torch.randn(B, len(frame_ids) - 1, H, W, device=device)
+                                                for _ in range(4)] if graph else None)["loss"]
 
     state = {"i": 0}
 
@@ -163,4 +180,37 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp):
         opt.step()
         return loss
 
-    return step, B
+    if not graph:
+        return step, B
+
+    static = {k: v.clone() for k, v in batches[0].items()}
+
+    def body():
+        outputs = model(static, frame_ids)
+        loss = loss_fn(static, outputs)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            body()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    opt.zero_grad(set_to_none=True)
+    with torch.cuda.graph(g):
+        static_loss = body()
+
+    def graphed_step():
+        batch = batches[state["i"] % len(batches)]
+        state["i"] += 1
+        for k, v in batch.items():
+            static[k].copy_(v)
+        g.replay()
+        return static_loss
+
+    return graphed_step, B
