@@ -315,10 +315,10 @@ static cudaError_t launch_tiles(const Params& p, cudaStream_t st) {
 template <bool BWD, int MM>
 static cudaError_t dispatch_tiles_s(const Params& p, cudaStream_t st) {
   switch (p.S) {
-    case 1: return launch_tiles<Tile<1, BWD, kTW, tile_h(1), tile_nt(1), MM>>(p, st);
-    case 2: return launch_tiles<Tile<2, BWD, kTW, tile_h(2), tile_nt(2), MM>>(p, st);
-    case 3: return launch_tiles<Tile<3, BWD, kTW, tile_h(3), tile_nt(3), MM>>(p, st);
-    default: return launch_tiles<Tile<4, BWD, kTW, tile_h(4), tile_nt(4), MM>>(p, st);
+    case 1: return launch_tiles<Tile<1, BWD, kTW, tile_h(1), tile_nt(1, BWD), MM>>(p, st);
+    case 2: return launch_tiles<Tile<2, BWD, kTW, tile_h(2), tile_nt(2, BWD), MM>>(p, st);
+    case 3: return launch_tiles<Tile<3, BWD, kTW, tile_h(3), tile_nt(3, BWD), MM>>(p, st);
+    default: return launch_tiles<Tile<4, BWD, kTW, tile_h(4), tile_nt(4, BWD), MM>>(p, st);
   }
 }
 template <bool BWD>

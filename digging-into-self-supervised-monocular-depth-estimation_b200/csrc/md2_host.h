@@ -31,9 +31,10 @@ constexpr int kNT = MD2_NT;
 // Tile height per source count: the backward build keeps S-proportional buffers in shared memory, so the
 // tile shrinks with S to keep two CTAs resident per SM (<= ~113 KB each).
 constexpr int tile_h(int S) { return S <= 2 ? kTH : (S == 3 ? (kTH * 3) / 4 : kTH / 2); }
-// Threads per CTA: 10 warps measured 1.3 % faster than 8 for the 32x16 tile (phase B then runs exactly two
-// window rows per warp); the smaller tiles of S >= 3 keep 8.
-constexpr int tile_nt(int S) { return (S <= 2 && kNT == 256) ? 320 : kNT; }
+// Threads per CTA: with the backward, 10 warps measured 1.3 % faster than 8 for the 32x16 tile (0.750 vs
+// 0.761 ms); the forward-only build is much slower with 10 (584 vs 421 us under ncu: it no longer fits
+// three CTAs per SM) and the smaller tiles of S >= 3 keep 8.
+constexpr int tile_nt(int S, bool bwd) { return (bwd && S <= 2 && kNT == 256) ? 320 : kNT; }
 
 enum Mode { kForward = 0, kFused = 1, kBackward = 2 };
 

@@ -51,10 +51,10 @@ static void run_tiles(const Params& p) {
 template <bool BWD, int MM>
 static void dispatch_tiles_s(const Params& p) {
   switch (p.S) {
-    case 1: run_tiles<Tile<1, BWD, kTW, tile_h(1), tile_nt(1), MM>>(p); break;
-    case 2: run_tiles<Tile<2, BWD, kTW, tile_h(2), tile_nt(2), MM>>(p); break;
-    case 3: run_tiles<Tile<3, BWD, kTW, tile_h(3), tile_nt(3), MM>>(p); break;
-    default: run_tiles<Tile<4, BWD, kTW, tile_h(4), tile_nt(4), MM>>(p); break;
+    case 1: run_tiles<Tile<1, BWD, kTW, tile_h(1), tile_nt(1, BWD), MM>>(p); break;
+    case 2: run_tiles<Tile<2, BWD, kTW, tile_h(2), tile_nt(2, BWD), MM>>(p); break;
+    case 3: run_tiles<Tile<3, BWD, kTW, tile_h(3), tile_nt(3, BWD), MM>>(p); break;
+    default: run_tiles<Tile<4, BWD, kTW, tile_h(4), tile_nt(4, BWD), MM>>(p); break;
   }
 }
 template <bool BWD>
