@@ -116,6 +116,11 @@ def test_cabi_against_reference_golden(cl, name):
     (1, 64, 96, [0, -1, 1], True, "smooth", "floor", 14),
     # ... unless the right-hand matrix has >= 786432 elements, where it is an FMA chain again
     (1, 320, 1024, [0, -1, 1], False, "smooth", "monodepth2", 15),   # 3*H*W and 4*H*W above the threshold
+    # partial tiles at the right / bottom edge (H, W multiples of 8 only), TMA boxes reaching outside the image
+    (2, 40, 72, [0, -1, 1], True, "iid", "monodepth2", 17),
+    (2, 104, 168, [0, -1, 1, "s"], True, "smooth", "monodepth2", 18),
+    (2, 200, 648, [0, 1], True, "iid", "floor", 19),
+    (2, 88, 136, [0, -1, 1, "s", 2], False, "smooth", "monodepth2", 20),
 ])
 def test_cabi_forward_bit_exact_vs_fp32_reference_on_gpu(cl, B, H, W, frame_ids, automask, kind, kv, seed):
     args = synth_args(B, H, W, frame_ids, automask, kind, seed, k_variant=kv)
