@@ -71,7 +71,13 @@ OPS_PROTOTYPES = {
     "md2_mean_inv_depth_forward": [_I, _I, _V, _V, _V],
     "md2_mean_inv_depth_backward": [_I, _I, _V, _V, _V, _V],
 }
-EXPORTS += list(OPS_PROTOTYPES) + ["md2_metrics_workspace_bytes", "md2_depth_metrics"]
+EXPORTS += list(OPS_PROTOTYPES) + ["md2_metrics_workspace_bytes", "md2_depth_metrics", "md2_pyramid_tables_bytes",
+                                   "md2_pyramid_tables_fill", "md2_pyramid_workspace_bytes", "md2_color_pyramid"]
+
+
+class md2_pyramid_cfg(C.Structure):
+    """include/md2_pipeline.h"""
+    _fields_ = [("N", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("H", C.c_int), ("W", C.c_int), ("scales", C.c_int)]
 
 
 class md2_metrics_cfg(C.Structure):
@@ -131,6 +137,14 @@ def load_library(path=None):
     lib.md2_depth_metrics.restype = C.c_int
     lib.md2_depth_metrics.argtypes = [C.POINTER(md2_metrics_cfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]
+    for name in ("md2_pyramid_tables_bytes", "md2_pyramid_workspace_bytes"):
+        getattr(lib, name).restype = C.c_size_t
+        getattr(lib, name).argtypes = [C.POINTER(md2_pyramid_cfg)]
+    lib.md2_pyramid_tables_fill.restype = C.c_int
+    lib.md2_pyramid_tables_fill.argtypes = [C.POINTER(md2_pyramid_cfg), C.c_void_p]
+    lib.md2_color_pyramid.restype = C.c_int
+    lib.md2_color_pyramid.argtypes = [C.POINTER(md2_pyramid_cfg), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
     for name, argtypes in OPS_PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -113,6 +113,9 @@ def interpolate(tensor, height, width, mode, align_corners):
 class _GridSample(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, grid):
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("md2_b200.grid_sample: the sampled image is data on the reference's path "
+                                      "(processor.py:172-176); no gradient with respect to it")
         img, grid = _f32(img, "grid_sample"), _f32(grid, "grid_sample")
         B, Cc, H, W = img.shape
         if grid.dim() != 4 or grid.shape[0] != B or grid.shape[3] != 2:
@@ -128,9 +131,6 @@ class _GridSample(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         img, grid = ctx.saved_tensors
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("md2_b200.grid_sample: the sampled image is data on the reference's path "
-                                      "(processor.py:172-176); no gradient with respect to it")
         B, Cc, H, W = img.shape
         g = g.contiguous()
         gg = torch.empty_like(grid)
@@ -189,6 +189,8 @@ class Depth2PointCloud(nn.Module):
 class _Project(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cam, K, T, B, H, W, eps):
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("md2_b200.PointCloud2Pixel: the intrinsics are data (processor.py:166-170)")
         cam, K, T = _f32(cam, "PointCloud2Pixel"), _f32(K, "PointCloud2Pixel"), _f32(T, "PointCloud2Pixel")
         if tuple(cam.shape) != (B, 4, H * W) or tuple(K.shape) != (B, 4, 4) or tuple(T.shape) != (B, 4, 4):
             raise RuntimeError(f"PointCloud2Pixel: cam {tuple(cam.shape)}, K {tuple(K.shape)}, T {tuple(T.shape)} do "
@@ -204,8 +206,6 @@ class _Project(torch.autograd.Function):
     def backward(ctx, g):
         cam, K, T = ctx.saved_tensors
         B, H, W, eps = ctx.dims
-        if ctx.needs_input_grad[1]:
-            raise NotImplementedError("md2_b200.PointCloud2Pixel: the intrinsics are data (processor.py:166-170)")
         g = g.contiguous()
         g_cam, g_T = torch.empty_like(cam), torch.empty_like(T)
         with torch.cuda.device(cam.device):
@@ -230,6 +230,8 @@ class PointCloud2Pixel(nn.Module):
 class _Reprojection(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("md2_b200.ReprojectionLoss: the target is data (processor.py:192-204)")
         pred, target = _f32(pred, "ReprojectionLoss"), _f32(target, "ReprojectionLoss")
         if pred.shape != target.shape or pred.dim() != 4 or pred.shape[1] != 3:
             raise RuntimeError(f"ReprojectionLoss: expected two [B,3,H,W] tensors, got {tuple(pred.shape)} and "
@@ -244,8 +246,6 @@ class _Reprojection(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         pred, target = ctx.saved_tensors
-        if ctx.needs_input_grad[1]:
-            raise NotImplementedError("md2_b200.ReprojectionLoss: the target is data (processor.py:192-204)")
         B, _, H, W = pred.shape
         g = g.contiguous()
         gp = torch.empty_like(pred)

@@ -1,0 +1,97 @@
+"""On-device input pipeline: the colour pyramid the loss reads, built on the GPU from the
+decoded uint8 frames instead of by PIL in 12 loader workers.
+
+Mirrors KITTIMonoDataset_v2.__getitem__ / resize_intrinsic (model_loader/kitti_mono.py:283-288, 319-329,
+347-362) for the non-jittered branch: flip, transforms.Resize(.., Image.ANTIALIAS) from the original image to
+every level, transforms.ToTensor().  Bit-identical to Pillow (include/md2_pipeline.h explains why).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import cabi
+
+_lib = None
+
+
+def _L():
+    global _lib
+    if _lib is None:
+        _lib = cabi.load_library()
+    return _lib
+
+
+def pyramid_tables(N, Hin, Win, H, W, scales=4):
+    """Host-side Lanczos coefficient tables (int32 numpy array) - no GPU needed."""
+    cfg = cabi.md2_pyramid_cfg(N, Hin, Win, H, W, scales)
+    lib = _L()
+    nbytes = lib.md2_pyramid_tables_bytes(C.byref(cfg))
+    if nbytes == 0:
+        raise RuntimeError(f"pyramid_tables: invalid configuration {(N, Hin, Win, H, W, scales)}")
+    tab = np.empty(nbytes // 4, dtype=np.int32)
+    rc = lib.md2_pyramid_tables_fill(C.byref(cfg), C.c_void_p(tab.ctypes.data))
+    if rc != 0:
+        raise RuntimeError(f"md2_pyramid_tables_fill failed with code {rc}")
+    return cfg, tab
+
+
+class ColorPyramid:
+    """pyr = ColorPyramid(N, 375, 1242, 192, 640, device="cuda:0"); levels = pyr(images_u8, flip)
+    images_u8: uint8 CUDA tensor [N, Hin, Win, 3]; flip: None or bool/uint8 [N]; returns `scales` float32
+    tensors [N, 3, H >> s, W >> s], i.e. inputs[("color", f, s)] for the N = batch x frames images."""
+
+    def __init__(self, N, Hin, Win, height, width, scales=4, device="cuda"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ColorPyramid: CUDA device required; md2_b200 has no CPU path")
+        self.cfg, tab = pyramid_tables(N, Hin, Win, height, width, scales)
+        self.tables = torch.from_numpy(tab).to(self.device)
+        self.workspace = torch.empty(_L().md2_pyramid_workspace_bytes(C.byref(self.cfg)), dtype=torch.uint8,
+                                     device=self.device)
+        self.shape = (N, Hin, Win, 3)
+
+    def __call__(self, images, flip=None):
+        if not (isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.uint8
+                and tuple(images.shape) == self.shape):
+            raise RuntimeError(f"ColorPyramid: expected a uint8 CUDA tensor {self.shape}, got "
+                               f"{getattr(images, 'dtype', type(images))} {tuple(getattr(images, 'shape', ()))}")
+        images = images.contiguous()
+        if flip is not None:
+            flip = flip.to(device=images.device, dtype=torch.uint8).contiguous()
+            if flip.numel() != self.cfg.N:
+                raise RuntimeError("ColorPyramid: flip must have one entry per image")
+        c = self.cfg
+        outs = [torch.empty(c.N, 3, c.H >> s, c.W >> s, dtype=torch.float32, device=images.device) for s in range(c.scales)]
+        ptrs = (C.c_void_p * c.scales)(*[o.data_ptr() for o in outs])
+        with torch.cuda.device(images.device):
+            rc = _L().md2_color_pyramid(C.byref(c), C.c_void_p(images.data_ptr()),
+                                        C.c_void_p(flip.data_ptr() if flip is not None else 0),
+                                        C.c_void_p(self.tables.data_ptr()), ptrs, C.c_void_p(self.workspace.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"md2_color_pyramid failed with code {rc}")
+        return outs
+
+
+def resize_intrinsic(width, height, scales=4, variant="row1_width"):
+    """K / inv_K per level as the reference loaders build them (host, numpy): "row1_width" is
+    KITTIMonoDataset_v2.resize_intrinsic (kitti_mono.py:319-329, both rows scaled by the WIDTH, floor division),
+    "monodepth2" the KITTIMonoDataset variant (kitti_mono.py:203-206)."""
+    K = np.array([[0.58, 0, 0.5, 0], [0, 1.92, 0.5, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32)
+    out = {}
+    for s in range(scales):
+        Kc = K.copy()
+        if variant == "row1_width":
+            Kc[0, :] = Kc[0, :] * width // (2 ** s)
+            Kc[1, :] = Kc[1, :] * width // (2 ** s)
+        elif variant == "monodepth2":
+            Kc[0, :] *= width // (2 ** s)
+            Kc[1, :] *= height // (2 ** s)
+        else:
+            raise ValueError(variant)
+        out[("K", s)] = torch.from_numpy(Kc)
+        out[("inv_K", s)] = torch.from_numpy(np.linalg.pinv(Kc))
+    return out

@@ -124,6 +124,8 @@ def test_grid_sample(M, B, H, W):
     _close(torch.autograd.grad((out * cot).sum(), g1)[0], torch.autograd.grad((ref * cot).sum(), g2)[0], 1e-5)
     with pytest.raises(NotImplementedError):
         M.grid_sample(img, grid, "zeros", True)
+    with pytest.raises(NotImplementedError):   # the sampled image is data on the reference's path
+        M.grid_sample(img.clone().requires_grad_(True), grid, "border", True)
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 24, 32), (3, 192, 640), (1, 3, 3)])

@@ -1,0 +1,75 @@
+"""Colour pyramid: pins the numpy restatement of Pillow's resampler against Pillow itself and
+against vectors produced by the reference dataset's own resize / ToTensor objects (tests/golden/pyramid.npz),
+and checks the library's HOST coefficient tables (md2_pyramid_tables_fill, no GPU) against the restatement."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_DIR
+from oracle import oracle_resize as R
+
+
+def _golden():
+    return np.load(os.path.join(GOLDEN_DIR, "pyramid.npz"))
+
+
+def test_oracle_matches_reference_golden():
+    z = _golden()
+    img = z["image"]
+    for flip in (0, 1):
+        got = R.color_pyramid(img, 64, 192, 4, flip=bool(flip))
+        for s in range(4):
+            ref = z[f"color_f{flip}_s{s}"]
+            assert got[s].shape == ref.shape and got[s].dtype == ref.dtype
+            assert np.array_equal(got[s], ref), (flip, s, np.abs(got[s] - ref).max())
+
+
+@pytest.mark.parametrize("Hin,Win,H,W", [(375, 1242, 192, 640), (375, 1242, 24, 80), (100, 333, 64, 96), (64, 96, 64, 96),
+                                         (40, 50, 64, 96)])
+def test_oracle_matches_pillow(Hin, Win, H, W):
+    from PIL import Image
+    img = np.random.default_rng(Hin + W).integers(0, 256, (Hin, Win, 3), dtype=np.uint8)
+    ref = np.array(Image.fromarray(img).resize((W, H), Image.LANCZOS))
+    assert np.array_equal(R.resize_antialias(img, H, W), ref)
+
+
+def test_host_tables_match_oracle():
+    import md2_b200.build as b
+    import md2_b200.pipeline as P
+    b.build_cuda_library()
+    for (Hin, Win, H, W, scales) in [(375, 1242, 192, 640, 4), (370, 1226, 320, 1024, 4), (120, 400, 64, 192, 4), (64, 96, 64, 96, 1)]:
+        cfg, tab = P.pyramid_tables(3, Hin, Win, H, W, scales)
+        off = 0
+        for s in range(scales):
+            for (n_in, n_out) in ((Win, W >> s), (Hin, H >> s)):
+                bounds, kk, ksize = R.precompute_coeffs(n_in, n_out)
+                assert np.array_equal(tab[off:off + 2 * n_out].reshape(n_out, 2), bounds)
+                off += 2 * n_out
+                assert np.array_equal(tab[off:off + n_out * ksize].reshape(n_out, ksize), kk)
+                off += n_out * ksize
+        assert off == tab.size
+
+
+def test_pyramid_abi_validates_without_gpu():
+    import md2_b200.cabi as cabi
+    lib = cabi.load_library()
+    assert lib.md2_pyramid_tables_bytes(C.byref(cabi.md2_pyramid_cfg(0, 375, 1242, 192, 640, 4))) == 0
+    assert lib.md2_pyramid_tables_bytes(C.byref(cabi.md2_pyramid_cfg(1, 375, 1242, 192, 640, 5))) == 0
+    assert lib.md2_pyramid_workspace_bytes(C.byref(cabi.md2_pyramid_cfg(2, 375, 1242, 192, 640, 4))) == 2 * 375 * 640 * 3
+    cfg = cabi.md2_pyramid_cfg(1, 375, 1242, 192, 640, 4)
+    assert lib.md2_pyramid_tables_fill(C.byref(cfg), C.c_void_p(0)) == cabi.MD2_ERR_NULL
+    one = C.c_void_p(8)
+    outs = (C.c_void_p * 4)(8, 8, 8, 0)
+    assert lib.md2_color_pyramid(C.byref(cfg), one, None, one, outs, one, None) == cabi.MD2_ERR_NULL
+    assert lib.md2_color_pyramid(C.byref(cfg), one, None, one, outs, None, None) == cabi.MD2_ERR_WORKSPACE
+
+
+def test_intrinsics_match_reference_golden():
+    import md2_b200.pipeline as P
+    z = _golden()
+    intr = P.resize_intrinsic(192, 64, 4, "row1_width")
+    for s in range(4):
+        assert np.array_equal(intr[("K", s)].numpy(), z[f"K{s}"])
+        assert np.array_equal(intr[("inv_K", s)].numpy(), z[f"inv_K{s}"])
