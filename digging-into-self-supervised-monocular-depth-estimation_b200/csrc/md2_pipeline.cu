@@ -1,9 +1,16 @@
 // md2_pipeline.cu - on-device colour pyramid: flip + Pillow-exact antialiased resize of the
 // decoded uint8 image to every pyramid level + ToTensor, replacing kitti_mono.py:283-288,296-304,347-362.
 //
-// Host part: the Lanczos coefficient tables of Pillow's resampler (double precision, libm), one per axis
-// and level.  Device part: two integer passes per level (horizontal to uint8, vertical to float / 255).
-// Byte / integer work end to end; bound by HBM and the L1/L2 re-reads of the taps, no tensor cores.
+// Host part: the Lanczos coefficient tables of Pillow's resampler (double precision, libm), one per axis and
+// level.  Device part, all integer / byte work:
+//   to_planar   [N,Hin,Win,3] u8 -> [N*3*Hin][pitch] u8 planes (flip applied here), so that every later pass
+//               sees independent rows whose taps are contiguous bytes
+//   pyramid_h   per level: horizontal pass with dp4a.u32.s32 - four taps per instruction on aligned 32-bit words;
+//               the 23-bit fixed-point coefficients are split into three signed 8-bit digits
+//               (c = d0 + 2^8 d1 + 2^16 d2), one dp4a accumulator per digit, recombined exactly in int32
+//   pyramid_v   per level: vertical pass on four byte columns per thread (one 32-bit load per tap row),
+//               + ToTensor (/255) straight into the CHW float output (one 16-byte store)
+// Results are bit-identical to Pillow (tests/test_gpu_pipeline.py).
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -13,11 +20,15 @@
 namespace md2 {
 
 constexpr int kPrecisionBits = 32 - 8 - 2;  // Pillow: PRECISION_BITS
+constexpr int kRowsPerThread = 4;           // rows that share one set of coefficient loads in pyramid_h
 
-// ---- table layout: per level, X axis then Y axis; per axis [bounds: 2 * out ints][coeffs: out * ksize ints]
-struct AxisTab {
-  int in, out, ksize;
-  size_t offset;  // in ints from the start of the tables
+// ---- table layout (ints), per level:
+//   X axis: [w0: out] first aligned input word of each output pixel
+//           [cd: 3 digits][kw words][out]   packed signed 8-bit coefficient digits per aligned input word
+//   Y axis: [bounds: 2 * out][coeffs: out * ksize]   as in Pillow
+struct LevelTab {
+  int wout, hout, ksx, ksy, kw;
+  size_t x_w0, x_cd, y_bounds, y_coef;  // offsets in ints
 };
 
 static inline int lanczos_ksize(int in, int out) {
@@ -26,18 +37,27 @@ static inline int lanczos_ksize(int in, int out) {
   return (int)ceil(3.0 * fs) * 2 + 1;
 }
 
-static inline size_t pyramid_layout(const md2_pyramid_cfg& c, AxisTab tab[kMaxScales][2]) {
+MD2_HD int planar_pitch(int Win) { return ((Win + 3) / 4) * 4 + 4; }  // multiple of 4, >= Win + 4 (zero padded)
+
+static inline size_t pyramid_layout(const md2_pyramid_cfg& c, LevelTab tab[kMaxScales]) {
   size_t off = 0;
-  for (int s = 0; s < c.scales; ++s)
-    for (int a = 0; a < 2; ++a) {
-      AxisTab t;
-      t.in = a == 0 ? c.Win : c.Hin;
-      t.out = (a == 0 ? c.W : c.H) >> s;
-      t.ksize = lanczos_ksize(t.in, t.out);
-      t.offset = off;
-      off += (size_t)t.out * (2 + t.ksize);
-      if (tab) tab[s][a] = t;
-    }
+  for (int s = 0; s < c.scales; ++s) {
+    LevelTab t;
+    t.wout = c.W >> s;
+    t.hout = c.H >> s;
+    t.ksx = lanczos_ksize(c.Win, t.wout);
+    t.ksy = lanczos_ksize(c.Hin, t.hout);
+    t.kw = (t.ksx + 3) / 4 + 1;  // aligned words that can hold ksx consecutive bytes at any alignment
+    t.x_w0 = off;
+    off += t.wout;
+    t.x_cd = off;
+    off += (size_t)3 * t.kw * t.wout;
+    t.y_bounds = off;
+    off += 2 * (size_t)t.hout;
+    t.y_coef = off;
+    off += (size_t)t.hout * t.ksy;
+    if (tab) tab[s] = t;
+  }
   return off;
 }
 
@@ -46,7 +66,10 @@ static inline int validate_pyramid(const md2_pyramid_cfg* c) {
   if (c->N < 1 || c->Hin < 1 || c->Win < 1 || c->H < 1 || c->W < 1) return MD2_ERR_SHAPE;
   if (c->scales < 1 || c->scales > kMaxScales) return MD2_ERR_SHAPE;
   if ((c->H >> (c->scales - 1)) < 1 || (c->W >> (c->scales - 1)) < 1) return MD2_ERR_SHAPE;
-  if ((long long)c->N * c->Hin * c->Win * 3 > 0x7fffffffLL) return MD2_ERR_SHAPE;
+  if ((long long)c->N * 3 * c->Hin * planar_pitch(c->Win) > 0x7fffffffLL) return MD2_ERR_SHAPE;
+  if ((long long)c->N * 3 * c->Hin > 65535LL * kRowsPerThread || c->Hin > 65535 || c->N > 21845) return MD2_ERR_SHAPE;  // grid.y / .z
+  if (lanczos_ksize(c->Win, c->W >> (c->scales - 1)) > 1024 || lanczos_ksize(c->Hin, c->H >> (c->scales - 1)) > 1024)
+    return MD2_ERR_SHAPE;
   return 0;
 }
 
@@ -60,34 +83,61 @@ static inline double lanczos3(double x) {
   return 0.0;
 }
 
-// Pillow's precompute_coeffs + normalize_coeffs_8bpc for one axis (box = the whole image)
-static void fill_axis(const AxisTab& t, int* base) {
-  int* bounds = base + t.offset;
-  int* kk = bounds + 2 * (size_t)t.out;
-  const double scale = (double)t.in / (double)t.out;
+// Pillow's precompute_coeffs + normalize_coeffs_8bpc for one output position (box = the whole image)
+static void axis_coeffs(int in, int out, int xx, int ksize, int* k, int& xmin, int& cnt) {
+  const double scale = (double)in / (double)out;
   const double fs = scale < 1.0 ? 1.0 : scale;
   const double support = 3.0 * fs, ss = 1.0 / fs;
+  const double center = (xx + 0.5) * scale;
   double w[1024];
-  for (int xx = 0; xx < t.out; ++xx) {
-    const double center = (xx + 0.5) * scale;
-    int xmin = (int)(center - support + 0.5);
-    if (xmin < 0) xmin = 0;
-    int xmax = (int)(center + support + 0.5);
-    if (xmax > t.in) xmax = t.in;
-    xmax -= xmin;
-    double ww = 0.0;
-    for (int x = 0; x < xmax; ++x) {
-      w[x] = lanczos3((x + xmin - center + 0.5) * ss);
-      ww += w[x];
+  xmin = (int)(center - support + 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)(center + support + 0.5);
+  if (xmax > in) xmax = in;
+  cnt = xmax - xmin;
+  double ww = 0.0;
+  for (int x = 0; x < cnt; ++x) {
+    w[x] = lanczos3((x + xmin - center + 0.5) * ss);
+    ww += w[x];
+  }
+  for (int x = 0; x < ksize; ++x) {
+    double v = x < cnt ? w[x] : 0.0;
+    if (x < cnt && ww != 0.0) v /= ww;
+    k[x] = v < 0 ? (int)(-0.5 + v * (1 << kPrecisionBits)) : (int)(0.5 + v * (1 << kPrecisionBits));
+  }
+}
+
+static void fill_level(const md2_pyramid_cfg& c, const LevelTab& t, int* base) {
+  int k[1024];
+  // Y axis: Pillow's layout
+  for (int y = 0; y < t.hout; ++y) {
+    int ymin, cnt;
+    axis_coeffs(c.Hin, t.hout, y, t.ksy, k, ymin, cnt);
+    base[t.y_bounds + 2 * y] = ymin;
+    base[t.y_bounds + 2 * y + 1] = cnt;
+    for (int j = 0; j < t.ksy; ++j) base[t.y_coef + (size_t)y * t.ksy + j] = k[j];
+  }
+  // X axis: per aligned input word, three packed signed-digit words
+  for (int x = 0; x < t.wout; ++x) {
+    int xmin, cnt;
+    axis_coeffs(c.Win, t.wout, x, t.ksx, k, xmin, cnt);
+    const int w0 = xmin >> 2;
+    base[t.x_w0 + x] = w0;
+    for (int w = 0; w < t.kw; ++w) {
+      unsigned packed[3] = {0u, 0u, 0u};
+      for (int b = 0; b < 4; ++b) {
+        const int j = 4 * (w0 + w) + b - xmin;
+        const int cf = (j >= 0 && j < cnt) ? k[j] : 0;
+        const int d0 = ((cf + 128) & 255) - 128;
+        const int c1 = (cf - d0) >> 8;
+        const int d1 = ((c1 + 128) & 255) - 128;
+        const int d2 = (c1 - d1) >> 8;  // |cf| < 2^23  =>  |d2| <= 64
+        packed[0] |= (unsigned)(d0 & 255) << (8 * b);
+        packed[1] |= (unsigned)(d1 & 255) << (8 * b);
+        packed[2] |= (unsigned)(d2 & 255) << (8 * b);
+      }
+      for (int d = 0; d < 3; ++d) base[t.x_cd + ((size_t)d * t.kw + w) * t.wout + x] = (int)packed[d];
     }
-    int* k = kk + (size_t)xx * t.ksize;
-    for (int x = 0; x < t.ksize; ++x) {
-      double v = x < xmax ? w[x] : 0.0;
-      if (x < xmax && ww != 0.0) v /= ww;
-      k[x] = v < 0 ? (int)(-0.5 + v * (1 << kPrecisionBits)) : (int)(0.5 + v * (1 << kPrecisionBits));
-    }
-    bounds[2 * xx] = xmin;
-    bounds[2 * xx + 1] = xmax;
   }
 }
 
@@ -96,62 +146,133 @@ __device__ __forceinline__ int clip8(int v) {
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-// horizontal pass: [N, Hin, Win, 3] u8 -> [N, Hin, Wout, 3] u8
-__global__ void __launch_bounds__(256) pyramid_h(int N, int Hin, int Win, int Wout, int ksize, const uint8_t* __restrict__ img,
-                                                 const uint8_t* __restrict__ flip, const int* __restrict__ tab, uint8_t* tmp) {
-  const int* bounds = tab;
-  const int* kk = tab + 2 * Wout;
-  const long long total = (long long)N * Hin * Wout;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const int x = (int)(i % Wout);
-    const long long row = i / Wout;  // n * Hin + y
-    const int n = (int)(row / Hin);
-    const int xmin = bounds[2 * x], cnt = bounds[2 * x + 1];
-    const int* k = kk + (size_t)x * ksize;
-    const uint8_t* src = img + row * (long long)Win * 3;
-    const bool fl = flip && flip[n];
-    int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-    for (int j = 0; j < cnt; ++j) {
-      const int xs = fl ? Win - 1 - (xmin + j) : xmin + j;
-      const uint8_t* px = src + xs * 3;
-      const int c = k[j];
-      s0 += px[0] * c;
-      s1 += px[1] * c;
-      s2 += px[2] * c;
+// v / 255 correctly rounded for the 256 possible byte values (transforms.ToTensor's .div(255)): one Newton
+// correction of v * fl(1/255); equal to IEEE division for every v in [0, 255] (tests/test_gpu_pipeline.py compares
+// every output value with Pillow + ToTensor)
+__device__ __forceinline__ float div255(int v) {
+  const float r = 1.0f / 255.0f, x = (float)v;
+  const float q = __fmul_rn(x, r);
+  return __fmaf_rn(__fmaf_rn(-255.0f, q, x), r, q);
+}
+
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// All index arithmetic below is 32-bit (validate_pyramid bounds every extent by 2^31) and the row / plane
+// coordinates come from blockIdx.y / .z: 64-bit divisions were 2/3 of the instructions of the first version.
+
+// [N,Hin,Win,3] u8 -> planar rows [(n*3 + c)*Hin + y][pitch], flipped if asked, zero padded.
+// grid (words / 128, Hin, N); a thread turns 4 RGB pixels (12 bytes) into one word of each plane.
+__global__ void __launch_bounds__(128) pyramid_to_planar(int Hin, int Win, int pitch, const uint8_t* __restrict__ img,
+                                                         const uint8_t* __restrict__ flip, unsigned* planar) {
+  const int pw = pitch >> 2;
+  const int w = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  if (w >= pw) return;
+  const uint8_t* src = img + ((size_t)n * Hin + y) * Win * 3;
+  const bool fl = flip && flip[n];
+  unsigned v[3] = {0u, 0u, 0u};
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int x = 4 * w + b;
+    if (x < Win) {
+      const uint8_t* px = src + (fl ? Win - 1 - x : x) * 3;
+      v[0] |= (unsigned)px[0] << (8 * b);
+      v[1] |= (unsigned)px[1] << (8 * b);
+      v[2] |= (unsigned)px[2] << (8 * b);
     }
-    uint8_t* o = tmp + i * 3;
-    o[0] = (uint8_t)clip8(s0);
-    o[1] = (uint8_t)clip8(s1);
-    o[2] = (uint8_t)clip8(s2);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) planar[((size_t)(n * 3 + c) * Hin + y) * pw + w] = v[c];
+}
+
+// horizontal pass on planar rows: [rows][pitch] u8 -> [rows][wout] u8.  grid (wout / 128, row groups); a thread owns
+// one x_out of kRowsPerThread consecutive rows, so that its three coefficient words per input word are loaded once
+template <int KW>
+__global__ void __launch_bounds__(128) pyramid_h(int rows, int pitch, int wout, int kw_rt, const unsigned* __restrict__ planar,
+                                                 const int* __restrict__ w0_tab, const int* __restrict__ cd, uint8_t* tmp) {
+  const int kw = KW > 0 ? KW : kw_rt;
+  const int pw = pitch >> 2;
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  if (x >= wout) return;
+  const int r0 = blockIdx.y * kRowsPerThread;
+  int a0[kRowsPerThread], a1[kRowsPerThread], a2[kRowsPerThread];
+  const unsigned* src[kRowsPerThread];
+  const int w0 = w0_tab[x];
+#pragma unroll
+  for (int r = 0; r < kRowsPerThread; ++r) {
+    a0[r] = a1[r] = a2[r] = 0;
+    src[r] = planar + (size_t)imin(r0 + r, rows - 1) * pw + w0;
+  }
+  const int* c0p = cd + x;
+  const int* c1p = c0p + kw * wout;
+  const int* c2p = c1p + kw * wout;
+#pragma unroll
+  for (int w = 0; w < (KW > 0 ? KW : 1); ++w) {
+    for (int ww = w; ww < kw; ww += (KW > 0 ? kw : 1)) {  // compile-time trip count when KW > 0, run-time loop otherwise
+      const int c0 = c0p[ww * wout], c1 = c1p[ww * wout], c2 = c2p[ww * wout];
+#pragma unroll
+      for (int r = 0; r < kRowsPerThread; ++r) {
+        const unsigned px = src[r][ww];
+        a0[r] = dp4a_us(px, c0, a0[r]);
+        a1[r] = dp4a_us(px, c1, a1[r]);
+        a2[r] = dp4a_us(px, c2, a2[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kRowsPerThread; ++r)
+    if (r0 + r < rows) {
+      // exact modulo 2^32, and the true sum fits int32 (Pillow relies on the same bound)
+      const unsigned ss = (1u << (kPrecisionBits - 1)) + (unsigned)a0[r] + (unsigned)a1[r] * 256u + (unsigned)a2[r] * 65536u;
+      tmp[(size_t)(r0 + r) * wout + x] = (uint8_t)clip8((int)ss);
+    }
+}
+
+// vertical pass + ToTensor on planar rows: [(n*3+c)*Hin + y][wout] u8 -> [N,3,hout,wout] f32; VEC byte columns per
+// thread.  grid (hout * (wout / VEC) / 128, planes)
+template <int VEC>
+__global__ void __launch_bounds__(128) pyramid_v(int Hin, int hout, int wout, int ksize, const uint8_t* __restrict__ tmp,
+                                                 const int* __restrict__ bounds, const int* __restrict__ kk, float* out) {
+  const int wv = wout / VEC;
+  const int i = blockIdx.x * 128 + threadIdx.x, pl = blockIdx.y;
+  if (i >= hout * wv) return;
+  const int y = i / wv, xv = i - y * wv;
+  const int ymin = bounds[2 * y], cnt = bounds[2 * y + 1];
+  const int* k = kk + y * ksize;
+  const uint8_t* src = tmp + ((size_t)pl * Hin + ymin) * wout + xv * VEC;
+  int acc[VEC];
+#pragma unroll
+  for (int b = 0; b < VEC; ++b) acc[b] = 1 << (kPrecisionBits - 1);
+  for (int j = 0; j < cnt; ++j) {
+    const int c = k[j];
+    if (VEC == 4) {
+      const unsigned px = *reinterpret_cast<const unsigned*>(src);
+      acc[0] += (int)__byte_perm(px, 0, 0x4440) * c;
+      acc[1] += (int)__byte_perm(px, 0, 0x4441) * c;
+      acc[2] += (int)__byte_perm(px, 0, 0x4442) * c;
+      acc[3] += (int)__byte_perm(px, 0, 0x4443) * c;
+    } else {
+      acc[0] += src[0] * c;
+    }
+    src += wout;
+  }
+  float* o = out + ((size_t)pl * hout + y) * wout + xv * VEC;  // transforms.ToTensor: uint8 -> float32, .div(255)
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(o) = make_float4(div255(clip8(acc[0])), div255(clip8(acc[1])), div255(clip8(acc[2])), div255(clip8(acc[3])));
+  } else {
+    o[0] = div255(clip8(acc[0]));
   }
 }
 
-// vertical pass + ToTensor: [N, Hin, Wout, 3] u8 -> [N, 3, Hout, Wout] f32 (/255)
-__global__ void __launch_bounds__(256) pyramid_v(int N, int Hin, int Hout, int Wout, int ksize, const uint8_t* __restrict__ tmp,
-                                                 const int* __restrict__ tab, float* out) {
-  const int* bounds = tab;
-  const int* kk = tab + 2 * Hout;
-  const long long total = (long long)N * Hout * Wout;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const int x = (int)(i % Wout), y = (int)((i / Wout) % Hout), n = (int)(i / ((long long)Wout * Hout));
-    const int ymin = bounds[2 * y], cnt = bounds[2 * y + 1];
-    const int* k = kk + (size_t)y * ksize;
-    const uint8_t* src = tmp + (((long long)n * Hin + ymin) * Wout + x) * 3;
-    int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-    for (int j = 0; j < cnt; ++j) {
-      const int c = k[j];
-      s0 += src[0] * c;
-      s1 += src[1] * c;
-      s2 += src[2] * c;
-      src += (long long)Wout * 3;
-    }
-    const long long plane = (long long)Hout * Wout;
-    float* o = out + (long long)n * 3 * plane + (long long)y * Wout + x;
-    o[0] = __fdiv_rn((float)clip8(s0), 255.0f);  // transforms.ToTensor: uint8 -> float32, .div(255)
-    o[plane] = __fdiv_rn((float)clip8(s1), 255.0f);
-    o[2 * plane] = __fdiv_rn((float)clip8(s2), 255.0f);
-  }
+template <int KW>
+static void launch_h(int rows, int pitch, const LevelTab& t, const unsigned* planar, const int* tables, uint8_t* tmp, cudaStream_t st) {
+  const dim3 grid((t.wout + 127) / 128, (rows + kRowsPerThread - 1) / kRowsPerThread);
+  pyramid_h<KW><<<grid, 128, 0, st>>>(rows, pitch, t.wout, t.kw, planar, tables + t.x_w0, tables + t.x_cd, tmp);
 }
+
 
 }  // namespace md2
 
@@ -168,19 +289,18 @@ int md2_pyramid_tables_fill(const md2_pyramid_cfg* cfg, void* host_tables) {
   const int v = validate_pyramid(cfg);
   if (v != 0) return v;
   if (!host_tables) return MD2_ERR_NULL;
-  AxisTab tab[kMaxScales][2];
+  LevelTab tab[kMaxScales];
   pyramid_layout(*cfg, tab);
-  for (int s = 0; s < cfg->scales; ++s)
-    for (int a = 0; a < 2; ++a) {
-      if (tab[s][a].ksize > 1024) return MD2_ERR_SHAPE;
-      fill_axis(tab[s][a], (int*)host_tables);
-    }
+  for (int s = 0; s < cfg->scales; ++s) fill_level(*cfg, tab[s], (int*)host_tables);
   return 0;
 }
 
 size_t md2_pyramid_workspace_bytes(const md2_pyramid_cfg* cfg) {
   if (validate_pyramid(cfg) != 0) return 0;
-  return (size_t)cfg->N * cfg->Hin * cfg->W * 3;  // level 0 is the widest intermediate
+  const size_t rows = (size_t)cfg->N * 3 * cfg->Hin;
+  // planar copy of the input (+ one word of slack) and the level-0 intermediate, both 256-byte aligned
+  const size_t planar = ((rows * planar_pitch(cfg->Win) + 4 * 1024 + 255) / 256) * 256;
+  return planar + ((rows * cfg->W + 255) / 256) * 256;
 }
 
 int md2_color_pyramid(const md2_pyramid_cfg* cfg, const uint8_t* images, const uint8_t* flip, const void* device_tables,
@@ -191,19 +311,32 @@ int md2_color_pyramid(const md2_pyramid_cfg* cfg, const uint8_t* images, const u
   if (!workspace) return MD2_ERR_WORKSPACE;
   for (int s = 0; s < cfg->scales; ++s)
     if (!out[s]) return MD2_ERR_NULL;
-  AxisTab tab[kMaxScales][2];
+  LevelTab tab[kMaxScales];
   pyramid_layout(*cfg, tab);
   cudaStream_t st = (cudaStream_t)stream;
   const int* tables = (const int*)device_tables;
+  const int rows = cfg->N * 3 * cfg->Hin, pitch = planar_pitch(cfg->Win);
+  unsigned* planar = (unsigned*)workspace;
+  const size_t planar_bytes = (((size_t)rows * pitch + 4 * 1024 + 255) / 256) * 256;
+  uint8_t* tmp = (uint8_t*)workspace + planar_bytes;
+  // the slack after the last planar row is read (times zero coefficients) by the last rows' trailing words
+  cudaMemsetAsync((uint8_t*)workspace + (size_t)rows * pitch, 0, planar_bytes - (size_t)rows * pitch, st);
+  pyramid_to_planar<<<dim3(((pitch >> 2) + 127) / 128, cfg->Hin, cfg->N), 128, 0, st>>>(cfg->Hin, cfg->Win, pitch, images, flip, planar);
   for (int s = 0; s < cfg->scales; ++s) {
-    const AxisTab &tx = tab[s][0], &ty = tab[s][1];
-    const long long nh = (long long)cfg->N * cfg->Hin * tx.out, nv = (long long)cfg->N * ty.out * tx.out;
-    const int bh = (int)((nh + 255) / 256 > 148 * 16 ? 148 * 16 : (nh + 255) / 256);
-    const int bv = (int)((nv + 255) / 256 > 148 * 16 ? 148 * 16 : (nv + 255) / 256);
-    pyramid_h<<<bh, 256, 0, st>>>(cfg->N, cfg->Hin, cfg->Win, tx.out, tx.ksize, images, flip, tables + tx.offset,
-                                  (uint8_t*)workspace);
-    pyramid_v<<<bv, 256, 0, st>>>(cfg->N, cfg->Hin, ty.out, tx.out, ty.ksize, (const uint8_t*)workspace, tables + ty.offset,
-                                  out[s]);
+    const LevelTab& t = tab[s];
+    switch (t.kw) {  // the KITTI 375x1242 -> 192x640 pyramid has 5 / 8 / 14 / 25 words per output pixel
+      case 5: launch_h<5>(rows, pitch, t, planar, tables, tmp, st); break;
+      case 8: launch_h<8>(rows, pitch, t, planar, tables, tmp, st); break;
+      case 14: launch_h<14>(rows, pitch, t, planar, tables, tmp, st); break;
+      case 25: launch_h<25>(rows, pitch, t, planar, tables, tmp, st); break;
+      default: launch_h<0>(rows, pitch, t, planar, tables, tmp, st); break;
+    }
+    if (t.wout % 4 == 0)
+      pyramid_v<4><<<dim3((t.hout * (t.wout / 4) + 127) / 128, cfg->N * 3), 128, 0, st>>>(
+          cfg->Hin, t.hout, t.wout, t.ksy, tmp, tables + t.y_bounds, tables + t.y_coef, out[s]);
+    else
+      pyramid_v<1><<<dim3((t.hout * t.wout + 127) / 128, cfg->N * 3), 128, 0, st>>>(
+          cfg->Hin, t.hout, t.wout, t.ksy, tmp, tables + t.y_bounds, tables + t.y_coef, out[s]);
   }
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;

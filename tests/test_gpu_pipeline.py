@@ -58,3 +58,12 @@ def test_pyramid_matches_oracle_and_rejects_bad_input():
         pyr(torch.from_numpy(img).to(DEV).float())       # wrong dtype
     with pytest.raises(RuntimeError):
         P.ColorPyramid(1, 100, 333, 64, 96, 3, device="cpu")
+
+
+def test_every_byte_value_converts_like_totensor():
+    """uint8 -> float32 / 255 for all 256 values (an identity-size 'resize' is the identity on the bytes)."""
+    import md2_b200.pipeline as P
+    img = np.arange(256, dtype=np.uint8).repeat(3 * 4).reshape(1, 16, 64, 3)   # every value, all channels
+    out = P.ColorPyramid(1, 16, 64, 16, 64, 1, device=DEV)(torch.from_numpy(img).to(DEV))[0][0].cpu().numpy()
+    ref = img[0].transpose(2, 0, 1).astype(np.float32) / np.float32(255)
+    assert np.array_equal(out, ref)
