@@ -440,7 +440,7 @@ def run_train_step(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     step, imgs = ts.make_step(args.loss, B, H, W, FRAME_IDS, dev, ddp=world > 1, graph=args.graph,
-                               channels_last=args.channels_last)
+                               channels_last=args.channels_last, device_pipeline=args.device_pipeline)
     for _ in range(args.warmup):
         step()
     if world > 1:
@@ -463,7 +463,7 @@ def run_train_step(args):
         print(json.dumps({"metric": "train_images_per_sec", "value": imgs * world * args.steps / (ms * 1e-3),
                           "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                          "dtype": "f32", "data": "synthetic", "loss_impl": args.loss, "cuda_graph": bool(args.graph), "channels_last": bool(args.channels_last), "final_loss": float(loss.detach()),
+                          "dtype": "f32", "data": "synthetic", "loss_impl": args.loss, "cuda_graph": bool(args.graph), "channels_last": bool(args.channels_last), "device_pipeline": bool(args.device_pipeline), "final_loss": float(loss.detach()),
                           "config": {"workload": "mono training step: ResNet-18 depth + separate ResNet-18 pose net, "
                                                  "batch 12 per GPU, 192x640, frame_ids [0,-1,1], 4 scales, Adam, fp32",
                                      "parallelism": f"ddp{world}"},
@@ -481,6 +481,8 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="loss", choices=["loss", "train_step"])
     ap.add_argument("--loss", default="fused", choices=["fused", "eager"])
     ap.add_argument("--channels-last", action="store_true", help="train_step: NHWC activations in the cuDNN networks")
+    ap.add_argument("--device-pipeline", action="store_true",
+                    help="train_step: start from uint8 frames on the device (md2_b200.pipeline) and end with md2_b200.metrics")
     ap.add_argument("--graph", action="store_true", help="train_step: replay the whole step as one CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

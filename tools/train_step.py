@@ -120,10 +120,13 @@ def synthetic_batch(B, H, W, frame_ids, seed, device):
     return inputs
 
 
-def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_last=False):
+def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_last=False, device_pipeline=False):
     """Returns (step_fn, images_per_step).  loss_impl: 'fused' (md2_b200) or 'eager' (PyTorch ops).
     graph: capture forward + loss + backward + Adam in one CUDA graph (SURVEY.md 8f N3) and replay it per step;
-    the batch is copied into static input buffers on the device before every replay."""
+    the batch is copied into static input buffers on the device before every replay.
+    device_pipeline: every step starts from decoded uint8 frames [3B,375,1242,3] resident on the device, builds the
+    colour pyramid with md2_b200.pipeline and ends with md2_b200.metrics on a sparse 375x1242
+    ground truth (N2), i.e. the whole md2_b200 surface around the stock networks."""
     from types import SimpleNamespace
     nets = MonoNets().to(device)
     if channels_last:   # NHWC activations for the cuDNN convolutions (precision-neutral); the loss inputs stay NCHW
@@ -169,6 +172,41 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_
                                                 for _ in range(4)] if graph else None)["loss"]
 
     state = {"i": 0}
+
+    if device_pipeline:
+        if graph or loss_impl != "fused":
+            raise NotImplementedError("--device-pipeline: fused loss, no --graph")
+        import md2_b200.metrics as MM
+        import md2_b200.pipeline as MP
+        nf = len(frame_ids)
+        pyr = MP.ColorPyramid(B * nf, 375, 1242, H, W, 4, device=device)
+        gen = torch.Generator(device=device).manual_seed(1)
+        frames = [torch.randint(0, 256, (B * nf, 375, 1242, 3), generator=gen, device=device, dtype=torch.uint8)
+                  for _ in range(2)]
+        flip = (torch.rand(B, generator=gen, device=device) > 0.5).to(torch.uint8).repeat(nf)   # one draw per sample
+        gt = torch.zeros(B, 1, 375, 1242, device=device)
+        hit = torch.rand(B, 1, 375, 1242, generator=gen, device=device) < 0.05
+        gt[hit] = 1.0 + 79 * torch.rand(int(hit.sum()), generator=gen, device=device)
+        static_in = {k: v for k, v in batches[0].items() if k[0] in ("K", "inv_K")}
+
+        def step():
+            levels = pyr(frames[state["i"] % 2], flip)            # [nf*B, 3, h, w] per level, frame-major
+            state["i"] += 1
+            inputs = dict(static_in)
+            for i, f in enumerate(frame_ids):
+                for s in range(4):
+                    inputs[("color", f, s)] = levels[s][i * B:(i + 1) * B]
+                c0 = inputs[("color", f, 0)]
+                inputs[("color_aug", f, 0)] = c0.contiguous(memory_format=torch.channels_last) if channels_last else c0
+            outputs = model(inputs, frame_ids)
+            loss = loss_fn(inputs, outputs)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            state["metrics"] = MM.depth_metrics(outputs[("depth", 0, 0)], gt)   # stays on the device
+            return loss
+
+        return step, B
 
     def step():
         inputs = batches[state["i"] % len(batches)]
