@@ -191,9 +191,10 @@ struct GradTPtrs {
 };
 
 // block 0: the scalar loss; blocks 1 + (f * B + b): dL/dT_f[b] = K_b^T (sum over the image's tiles of dL/dP)
-__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ Params p, float* loss, GradTPtrs gT,
-                                                       int want_grad_T) {
-  __shared__ double red[256];
+constexpr int kFinNT = 1024;  // block 0 is latency bound (dependent loads, fp64 divisions): 32 warps instead of 8
+__global__ void __launch_bounds__(kFinNT) finalize_kernel(const __grid_constant__ Params p, float* loss, GradTPtrs gT,
+                                                          int want_grad_T) {
+  __shared__ double red[kFinNT];
   __shared__ float part[21 * 12];
   __shared__ float dPs[12];
   const int t = threadIdx.x;
@@ -202,11 +203,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ P
     // photometric part: per-CTA partial sums, thread-strided in double
     double acc = 0.0;
     const double inv_n = 1.0 / ((double)p.B * p.H * p.W);
-    for (int i = t; i < p.n_tiles * kMaxScales; i += 256)
+    for (int i = t; i < p.n_tiles * kMaxScales; i += kFinNT)
       if ((i % kMaxScales) < p.ns) acc += (double)p.tile_loss[i] * inv_n;
     // smoothness part: one warp per (scale, image), lanes stride the row bands, fixed-order shuffle tree
     const int warp = t >> 5, lane = t & 31;
-    for (int pair = warp; pair < p.ns * p.B; pair += 8) {
+    for (int pair = warp; pair < p.ns * p.B; pair += kFinNT / 32) {
       const int s = pair / p.B, b = pair - s * p.B;
       const float* part = p.smooth_part + ((size_t)b * smooth_total(p.ns) + smooth_offset(s)) * 3;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ P
     }
     red[t] = acc / (double)p.ns;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {  // fixed-shape tree: deterministic
+    for (int o = kFinNT / 2; o > 0; o >>= 1) {  // fixed-shape tree: deterministic
       if (t < o) red[t] += red[t + o];
       __syncthreads();
     }
@@ -414,7 +415,7 @@ static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs*
   if (g_side_enabled && (ce = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return (int)ce;
   GradTPtrs gT;
   for (int f = 0; f < kMaxS; ++f) gT.p[f] = (g && f < cfg->S) ? g->grad_T[f] : nullptr;
-  finalize_kernel<<<1 + (mode != kForward ? p.B * p.S : 0), 256, 0, st>>>(p, mode == kBackward ? nullptr : out->loss, gT,
+  finalize_kernel<<<1 + (mode != kForward ? p.B * p.S : 0), kFinNT, 0, st>>>(p, mode == kBackward ? nullptr : out->loss, gT,
                                                                             mode != kForward);
   ce = cudaGetLastError();
   return ce == cudaSuccess ? 0 : (int)ce;
