@@ -20,7 +20,7 @@
 namespace md2 {
 
 constexpr int kPrecisionBits = 32 - 8 - 2;  // Pillow: PRECISION_BITS
-constexpr int kRowsPerThread = 4;           // rows that share one set of coefficient loads in pyramid_h
+constexpr int kRowsPerThread = 8;           // rows that share one set of coefficient loads in pyramid_h
 
 // ---- table layout (ints), per level:
 //   X axis: [w0: out] first aligned input word of each output pixel
