@@ -25,10 +25,11 @@ constexpr int kRowsPerThread = 8;           // rows that share one set of coeffi
 // ---- table layout (ints), per level:
 //   X axis: [w0: out] first aligned input word of each output pixel
 //           [cd: 3 digits][kw words][out]   packed signed 8-bit coefficient digits per aligned input word
-//   Y axis: [bounds: 2 * out][coeffs: out * ksize]   as in Pillow
+//   Y axis: [bounds: 2 * out][coeffs: out * ksize]   as in Pillow (scalar fallback)
+//           [cd: out][ng groups of 4 tap rows][3 digits]   packed signed 8-bit digits of 4 consecutive taps
 struct LevelTab {
-  int wout, hout, ksx, ksy, kw;
-  size_t x_w0, x_cd, y_bounds, y_coef;  // offsets in ints
+  int wout, hout, ksx, ksy, kw, ng;
+  size_t x_w0, x_cd, y_bounds, y_coef, y_cd;  // offsets in ints
 };
 
 static inline int lanczos_ksize(int in, int out) {
@@ -56,6 +57,9 @@ static inline size_t pyramid_layout(const md2_pyramid_cfg& c, LevelTab tab[kMaxS
     off += 2 * (size_t)t.hout;
     t.y_coef = off;
     off += (size_t)t.hout * t.ksy;
+    t.ng = (t.ksy + 3) / 4;
+    t.y_cd = off;
+    off += (size_t)t.hout * t.ng * 3;
     if (tab) tab[s] = t;
   }
   return off;
@@ -107,8 +111,22 @@ static void axis_coeffs(int in, int out, int xx, int ksize, int* k, int& xmin, i
   }
 }
 
+// three signed 8-bit digits of four coefficients, packed little-endian: c = d0 + 2^8 d1 + 2^16 d2
+static void pack_digits(const int cf[4], unsigned packed[3]) {
+  packed[0] = packed[1] = packed[2] = 0u;
+  for (int b = 0; b < 4; ++b) {
+    const int d0 = ((cf[b] + 128) & 255) - 128;
+    const int c1 = (cf[b] - d0) >> 8;
+    const int d1 = ((c1 + 128) & 255) - 128;
+    const int d2 = (c1 - d1) >> 8;  // |cf| < 2^23  =>  |d2| <= 64
+    packed[0] |= (unsigned)(d0 & 255) << (8 * b);
+    packed[1] |= (unsigned)(d1 & 255) << (8 * b);
+    packed[2] |= (unsigned)(d2 & 255) << (8 * b);
+  }
+}
+
 static void fill_level(const md2_pyramid_cfg& c, const LevelTab& t, int* base) {
-  int k[1024];
+  int k[1024 + 4];
   // Y axis: Pillow's layout
   for (int y = 0; y < t.hout; ++y) {
     int ymin, cnt;
@@ -116,6 +134,13 @@ static void fill_level(const md2_pyramid_cfg& c, const LevelTab& t, int* base) {
     base[t.y_bounds + 2 * y] = ymin;
     base[t.y_bounds + 2 * y + 1] = cnt;
     for (int j = 0; j < t.ksy; ++j) base[t.y_coef + (size_t)y * t.ksy + j] = k[j];
+    for (int g = 0; g < t.ng; ++g) {
+      int cf[4];
+      unsigned packed[3];
+      for (int b = 0; b < 4; ++b) cf[b] = (4 * g + b < cnt) ? k[4 * g + b] : 0;
+      pack_digits(cf, packed);
+      for (int d = 0; d < 3; ++d) base[t.y_cd + ((size_t)y * t.ng + g) * 3 + d] = (int)packed[d];
+    }
   }
   // X axis: per aligned input word, three packed signed-digit words
   for (int x = 0; x < t.wout; ++x) {
@@ -124,18 +149,13 @@ static void fill_level(const md2_pyramid_cfg& c, const LevelTab& t, int* base) {
     const int w0 = xmin >> 2;
     base[t.x_w0 + x] = w0;
     for (int w = 0; w < t.kw; ++w) {
-      unsigned packed[3] = {0u, 0u, 0u};
+      unsigned packed[3];
+      int cf[4];
       for (int b = 0; b < 4; ++b) {
         const int j = 4 * (w0 + w) + b - xmin;
-        const int cf = (j >= 0 && j < cnt) ? k[j] : 0;
-        const int d0 = ((cf + 128) & 255) - 128;
-        const int c1 = (cf - d0) >> 8;
-        const int d1 = ((c1 + 128) & 255) - 128;
-        const int d2 = (c1 - d1) >> 8;  // |cf| < 2^23  =>  |d2| <= 64
-        packed[0] |= (unsigned)(d0 & 255) << (8 * b);
-        packed[1] |= (unsigned)(d1 & 255) << (8 * b);
-        packed[2] |= (unsigned)(d2 & 255) << (8 * b);
+        cf[b] = (j >= 0 && j < cnt) ? k[j] : 0;
       }
+      pack_digits(cf, packed);
       for (int d = 0; d < 3; ++d) base[t.x_cd + ((size_t)d * t.kw + w) * t.wout + x] = (int)packed[d];
     }
   }
@@ -267,6 +287,44 @@ __global__ void __launch_bounds__(128) pyramid_v(int Hin, int hout, int wout, in
   }
 }
 
+// The same vertical pass with dp4a: four tap rows of four byte columns are transposed in registers (8 PRMT) so
+// that each column's four taps sit in one word, then 3 digit dp4a per column.  Rows past the window carry zero
+// coefficients (they may belong to the next plane or to the slack behind the buffer).
+__global__ void __launch_bounds__(128) pyramid_v_dp4a(int Hin, int hout, int wout, int ng, const uint8_t* __restrict__ tmp,
+                                                      const int* __restrict__ bounds, const int* __restrict__ cd, float* out) {
+  const int wv = wout >> 2;
+  const int i = blockIdx.x * 128 + threadIdx.x, pl = blockIdx.y;
+  if (i >= hout * wv) return;
+  const int y = i / wv, xv = i - y * wv;
+  const int ymin = bounds[2 * y];
+  const int* c = cd + (size_t)y * ng * 3;
+  const unsigned* src = reinterpret_cast<const unsigned*>(tmp + ((size_t)pl * Hin + ymin) * wout) + xv;
+  int a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+  for (int g = 0; g < ng; ++g) {
+    const unsigned r0 = src[0], r1 = src[wv], r2 = src[2 * wv], r3 = src[3 * wv];
+    const int c0 = c[0], c1 = c[1], c2 = c[2];
+    const unsigned lo01 = __byte_perm(r0, r1, 0x5140), hi01 = __byte_perm(r0, r1, 0x7362);
+    const unsigned lo23 = __byte_perm(r2, r3, 0x5140), hi23 = __byte_perm(r2, r3, 0x7362);
+    const unsigned t[4] = {__byte_perm(lo01, lo23, 0x5410), __byte_perm(lo01, lo23, 0x7632), __byte_perm(hi01, hi23, 0x5410),
+                           __byte_perm(hi01, hi23, 0x7632)};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      a0[b] = dp4a_us(t[b], c0, a0[b]);
+      a1[b] = dp4a_us(t[b], c1, a1[b]);
+      a2[b] = dp4a_us(t[b], c2, a2[b]);
+    }
+    src += 4 * wv;
+    c += 3;
+  }
+  float v[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const unsigned ss = (1u << (kPrecisionBits - 1)) + (unsigned)a0[b] + (unsigned)a1[b] * 256u + (unsigned)a2[b] * 65536u;
+    v[b] = div255(clip8((int)ss));
+  }
+  *reinterpret_cast<float4*>(out + ((size_t)pl * hout + y) * wout + xv * 4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 template <int KW>
 static void launch_h(int rows, int pitch, const LevelTab& t, const unsigned* planar, const int* tables, uint8_t* tmp, cudaStream_t st) {
   const dim3 grid((t.wout + 127) / 128, (rows + kRowsPerThread - 1) / kRowsPerThread);
@@ -300,7 +358,9 @@ size_t md2_pyramid_workspace_bytes(const md2_pyramid_cfg* cfg) {
   const size_t rows = (size_t)cfg->N * 3 * cfg->Hin;
   // planar copy of the input (+ one word of slack) and the level-0 intermediate, both 256-byte aligned
   const size_t planar = ((rows * planar_pitch(cfg->Win) + 4 * 1024 + 255) / 256) * 256;
-  return planar + ((rows * cfg->W + 255) / 256) * 256;
+  // level-0 intermediate + slack rows that the dp4a vertical pass may touch behind the last plane (zero coefficients)
+  const size_t slack = (size_t)(lanczos_ksize(cfg->Hin, cfg->H >> (cfg->scales - 1)) + 8) * cfg->W;
+  return planar + ((rows * cfg->W + slack + 255) / 256) * 256;
 }
 
 int md2_color_pyramid(const md2_pyramid_cfg* cfg, const uint8_t* images, const uint8_t* flip, const void* device_tables,
@@ -332,8 +392,8 @@ int md2_color_pyramid(const md2_pyramid_cfg* cfg, const uint8_t* images, const u
       default: launch_h<0>(rows, pitch, t, planar, tables, tmp, st); break;
     }
     if (t.wout % 4 == 0)
-      pyramid_v<4><<<dim3((t.hout * (t.wout / 4) + 127) / 128, cfg->N * 3), 128, 0, st>>>(
-          cfg->Hin, t.hout, t.wout, t.ksy, tmp, tables + t.y_bounds, tables + t.y_coef, out[s]);
+      pyramid_v_dp4a<<<dim3((t.hout * (t.wout / 4) + 127) / 128, cfg->N * 3), 128, 0, st>>>(
+          cfg->Hin, t.hout, t.wout, t.ng, tmp, tables + t.y_bounds, tables + t.y_cd, out[s]);
     else
       pyramid_v<1><<<dim3((t.hout * t.wout + 127) / 128, cfg->N * 3), 128, 0, st>>>(
           cfg->Hin, t.hout, t.wout, t.ksy, tmp, tables + t.y_bounds, tables + t.y_coef, out[s]);

@@ -52,6 +52,13 @@ def test_pyramid_matches_oracle_and_rejects_bad_input():
     ref = R.color_pyramid(img[0], 64, 96, 3)
     for s in range(3):
         assert np.array_equal(levels[s][0].cpu().numpy(), ref[s])
+    # a level whose width is not a multiple of 4 takes the scalar vertical pass (200, 100, 50)
+    img2 = rng.integers(0, 256, (2, 90, 301, 3), dtype=np.uint8)
+    lv2 = P.ColorPyramid(2, 90, 301, 40, 200, 3, device=DEV)(torch.from_numpy(img2).to(DEV), torch.tensor([1, 0]))
+    for n, fl in ((0, True), (1, False)):
+        ref2 = R.color_pyramid(img2[n], 40, 200, 3, flip=fl)
+        for s in range(3):
+            assert np.array_equal(lv2[s][n].cpu().numpy(), ref2[s]), (n, s)
     with pytest.raises(RuntimeError):
         pyr(torch.from_numpy(img))                       # host tensor
     with pytest.raises(RuntimeError):

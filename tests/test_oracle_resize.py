@@ -67,6 +67,14 @@ def test_host_tables_match_oracle():
             off += 2 * hout
             assert np.array_equal(tab[off:off + hout * ksy].reshape(hout, ksy), ky)
             off += hout * ksy
+            ng = (ksy + 3) // 4                                      # the same taps, digit-packed four rows at a time
+            ycd = tab[off:off + hout * ng * 3].reshape(hout, ng, 3)
+            off += hout * ng * 3
+            yd = np.stack([((ycd.view(np.uint32) >> (8 * bb)) & 255).astype(np.uint8).view(np.int8).astype(np.int64)
+                           for bb in range(4)], -1)                  # [hout, ng, 3, 4]
+            ycoef = (yd[:, :, 0] + 256 * yd[:, :, 1] + 65536 * yd[:, :, 2]).reshape(hout, ng * 4)
+            for y in range(hout):
+                assert np.array_equal(ycoef[y, :by[y, 1]], ky[y, :by[y, 1]]) and not ycoef[y, by[y, 1]:].any()
         assert off == tab.size
 
 
