@@ -72,7 +72,14 @@ OPS_PROTOTYPES = {
     "md2_mean_inv_depth_backward": [_I, _I, _V, _V, _V, _V],
 }
 EXPORTS += list(OPS_PROTOTYPES) + ["md2_metrics_workspace_bytes", "md2_depth_metrics", "md2_pyramid_tables_bytes",
-                                   "md2_pyramid_tables_fill", "md2_pyramid_workspace_bytes", "md2_color_pyramid"]
+                                   "md2_pyramid_tables_fill", "md2_pyramid_workspace_bytes", "md2_color_pyramid",
+                                   "md2_jitter_workspace_bytes", "md2_color_jitter"]
+
+
+class md2_jitter_cfg(C.Structure):
+    """include/md2_pipeline.h"""
+    _fields_ = [("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("order", C.c_int * 4),
+                ("brightness", C.c_double), ("contrast", C.c_double), ("saturation", C.c_double), ("hue", C.c_double)]
 
 
 class md2_pyramid_cfg(C.Structure):
@@ -140,6 +147,10 @@ def load_library(path=None):
     for name in ("md2_pyramid_tables_bytes", "md2_pyramid_workspace_bytes"):
         getattr(lib, name).restype = C.c_size_t
         getattr(lib, name).argtypes = [C.POINTER(md2_pyramid_cfg)]
+    lib.md2_jitter_workspace_bytes.restype = C.c_size_t
+    lib.md2_jitter_workspace_bytes.argtypes = [C.POINTER(md2_jitter_cfg)]
+    lib.md2_color_jitter.restype = C.c_int
+    lib.md2_color_jitter.argtypes = [C.POINTER(md2_jitter_cfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.md2_pyramid_tables_fill.restype = C.c_int
     lib.md2_pyramid_tables_fill.argtypes = [C.POINTER(md2_pyramid_cfg), C.c_void_p]
     lib.md2_color_pyramid.restype = C.c_int

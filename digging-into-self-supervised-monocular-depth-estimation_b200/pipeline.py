@@ -2,8 +2,9 @@
 decoded uint8 frames instead of by PIL in 12 loader workers.
 
 Mirrors KITTIMonoDataset_v2.__getitem__ / resize_intrinsic (model_loader/kitti_mono.py:283-288, 319-329,
-347-362) for the non-jittered branch: flip, transforms.Resize(.., Image.ANTIALIAS) from the original image to
-every level, transforms.ToTensor().  Bit-identical to Pillow (include/md2_pipeline.h explains why).
+347-362): flip, transforms.Resize(.., Image.ANTIALIAS) from the original image to every level,
+transforms.ToTensor(), and the do_color branch (ColorJitter).  Bit-identical to Pillow / torchvision's PIL path
+(include/md2_pipeline.h explains why).
 """
 from __future__ import annotations
 
@@ -74,6 +75,55 @@ class ColorPyramid:
         if rc != 0:
             raise RuntimeError(f"md2_color_pyramid failed with code {rc}")
         return outs
+
+
+class ColorJitter:
+    """The jitter of KITTIMonoDataset_v2 (kitti_mono.py:281-282): ``ColorJitter.get_params((0.8, 1.2), (0.8, 1.2),
+    (0.8, 1.2), (-0.1, 0.1))`` draws the four factors and a shuffled order once, like torchvision <= 0.8 did, and
+    the object is then called on pyramid levels: float32 CUDA [N,3,h,w] (v/255) -> the same, bit-identical to the PIL
+    pipeline (uint8 between the four steps).  ``apply``: optional bool/uint8 [N], the per-sample do_color flag."""
+
+    OPS = ("brightness", "contrast", "saturation", "hue")
+
+    def __init__(self, order, brightness, contrast, saturation, hue):
+        self.order = [int(k) for k in order] + [-1] * (4 - len(order))
+        self.factors = (float(brightness), float(contrast), float(saturation), float(hue))
+
+    @staticmethod
+    def get_params(brightness, contrast, saturation, hue):
+        import random
+        order, f = [], [1.0, 1.0, 1.0, 0.0]
+        for k, rng in enumerate((brightness, contrast, saturation, hue)):   # torchvision 0.8 ColorJitter.get_params
+            if rng is not None:
+                f[k] = random.uniform(rng[0], rng[1])
+                order.append(k)
+        random.shuffle(order)
+        return ColorJitter(order, *f)
+
+    def __call__(self, images, apply=None):
+        if not (isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.float32 and images.dim() == 4
+                and images.shape[1] == 3):
+            raise RuntimeError("ColorJitter: expected a float32 CUDA tensor [N,3,H,W]; md2_b200 has no CPU path")
+        images = images.contiguous()
+        N, _, H, W = images.shape
+        cfg = cabi.md2_jitter_cfg(N, H, W, (C.c_int * 4)(*self.order), *self.factors)
+        lib = _L()
+        nbytes = lib.md2_jitter_workspace_bytes(C.byref(cfg))
+        if nbytes == 0:
+            raise RuntimeError(f"ColorJitter: invalid parameters {self.order} {self.factors}")
+        if apply is not None:
+            apply = apply.to(device=images.device, dtype=torch.uint8).contiguous()
+            if apply.numel() != N:
+                raise RuntimeError("ColorJitter: apply must have one entry per image")
+        with torch.cuda.device(images.device):
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=images.device)
+            out = torch.empty_like(images)
+            rc = lib.md2_color_jitter(C.byref(cfg), C.c_void_p(images.data_ptr()),
+                                      C.c_void_p(apply.data_ptr() if apply is not None else 0), C.c_void_p(out.data_ptr()),
+                                      C.c_void_p(ws.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"md2_color_jitter failed with code {rc}")
+        return out
 
 
 def resize_intrinsic(width, height, scales=4, variant="row1_width"):

@@ -4,7 +4,7 @@
  * (model_loader/kitti_mono.py:283-288, 296-304, 347-362): optional left-right flip of the decoded RGB
  * image, transforms.Resize(.., interpolation=Image.ANTIALIAS) from the ORIGINAL image to each of the
  * `scales` pyramid levels (H >> s, W >> s), and transforms.ToTensor() (uint8 HWC -> float32 CHW / 255).
- * The colour-jitter branch (do_color) is not covered: ("color_aug", f, s) equals ("color", f, s) here.
+ * The colour-jitter branch (do_color) is md2_color_jitter at the end of this header.
  *
  * The resampler is Pillow's (third-party, not part of /root/reference; Pillow 12.2.0,
  * src/libImaging/Resample.c: precompute_coeffs, normalize_coeffs_8bpc, ImagingResampleHorizontal_8bpc /
@@ -43,6 +43,22 @@ size_t md2_pyramid_workspace_bytes(const md2_pyramid_cfg* cfg);
 int md2_color_pyramid(const md2_pyramid_cfg* cfg, const uint8_t* images, const uint8_t* flip,
                       const void* device_tables, float* const* out /* [scales] host array of device pointers */,
                       void* workspace, md2_stream_t stream);
+
+/* Colour jitter of the do_color branch (model_loader/kitti_mono.py:281-282, 351-357): the four adjustments of
+ * torchvision's ColorJitter on uint8 images - brightness, contrast, saturation (Pillow ImageEnhance = Image.blend
+ * with a degenerate image), hue (Pillow RGB -> HSV, uint8 wrap-around shift, HSV -> RGB) - applied in `order`
+ * (op ids 0 brightness, 1 contrast, 2 saturation, 3 hue; -1 = skip), uint8 between the steps exactly like the PIL
+ * pipeline, bit-identical to it.  in / out: float32 [N,3,H,W] holding v/255 (a pyramid level); apply: uint8 [N]
+ * (0 = copy the image unchanged, the reference's do_color flag) or NULL. */
+typedef struct md2_jitter_cfg {
+  int N, H, W;
+  int order[4];
+  double brightness, contrast, saturation, hue; /* the Python floats torchvision draws; hue in [-0.5, 0.5] */
+} md2_jitter_cfg;
+
+size_t md2_jitter_workspace_bytes(const md2_jitter_cfg* cfg);
+int md2_color_jitter(const md2_jitter_cfg* cfg, const float* in, const uint8_t* apply, float* out, void* workspace,
+                     md2_stream_t stream);
 
 #ifdef __cplusplus
 }

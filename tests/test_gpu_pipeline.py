@@ -74,3 +74,49 @@ def test_every_byte_value_converts_like_totensor():
     out = P.ColorPyramid(1, 16, 64, 16, 64, 1, device=DEV)(torch.from_numpy(img).to(DEV))[0][0].cpu().numpy()
     ref = img[0].transpose(2, 0, 1).astype(np.float32) / np.float32(255)
     assert np.array_equal(out, ref)
+
+
+def _jitter_ref(img_u8, order, b, c, s, h):
+    import torchvision.transforms.functional as F
+    from PIL import Image
+    fn = (F.adjust_brightness, F.adjust_contrast, F.adjust_saturation, F.adjust_hue)
+    pil = Image.fromarray(img_u8)
+    for k in order:
+        pil = fn[k](pil, (b, c, s, h)[k])
+    return np.array(pil)
+
+
+def test_color_jitter_matches_golden_and_pil():
+    """do_color branch (kitti_mono.py:351-357): bit-identical to torchvision's PIL adjustments, uint8 between steps."""
+    import md2_b200.pipeline as P
+    z = np.load(os.path.join(GOLDEN_DIR, "jitter.npz"))
+    x = torch.from_numpy(z["image"].transpose(2, 0, 1).astype(np.float32) / np.float32(255))[None].to(DEV)
+    for i, row in enumerate(z["params"]):
+        out = P.ColorJitter([int(v) for v in row[:4]], *row[4:])(x)
+        got = np.round(out[0].cpu().numpy().transpose(1, 2, 0) * 255).astype(np.uint8)
+        assert np.array_equal(got, z[f"out{i}"]), i
+        assert np.array_equal(out[0].cpu().numpy(), z[f"out{i}"].transpose(2, 0, 1).astype(np.float32) / np.float32(255))
+    # random parameters at the training size, two images with different content, one of them switched off
+    rng = np.random.default_rng(9)
+    imgs = rng.integers(0, 256, (2, 192, 640, 3), dtype=np.uint8)
+    x = torch.from_numpy(imgs.transpose(0, 3, 1, 2).astype(np.float32) / np.float32(255)).to(DEV)
+    import random
+    random.seed(3)
+    for _ in range(6):
+        jit = P.ColorJitter.get_params((0.8, 1.2), (0.8, 1.2), (0.8, 1.2), (-0.1, 0.1))
+        out = jit(x, apply=torch.tensor([1, 0]))
+        got = np.round(out.cpu().numpy().transpose(0, 2, 3, 1) * 255).astype(np.uint8)
+        assert np.array_equal(got[0], _jitter_ref(imgs[0], jit.order, *jit.factors)), (jit.order, jit.factors)
+        assert np.array_equal(out[1].cpu().numpy(), x[1].cpu().numpy())
+
+
+def test_color_jitter_hsv_exhaustive():
+    """Every RGB colour through the hue adjustment (RGB -> HSV -> shift -> RGB) against Pillow."""
+    import md2_b200.pipeline as P
+    a = np.arange(256, dtype=np.uint8)
+    c = np.stack(np.meshgrid(a, a, a, indexing="ij"), -1).reshape(4096, 4096, 3)
+    x = torch.from_numpy(c.transpose(2, 0, 1).astype(np.float32) / np.float32(255))[None].to(DEV)
+    for hue in (0.0, 0.0837, -0.1):
+        out = P.ColorJitter([3], 1.0, 1.0, 1.0, hue)(x)
+        got = torch.round(out[0] * 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+        assert np.array_equal(got, _jitter_ref(c, [3], 1.0, 1.0, 1.0, hue)), hue
