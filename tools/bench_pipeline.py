@@ -38,6 +38,18 @@ def main():
         peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
+    # colour jitter of level 0 (the only jittered level the networks read), all 36 frames
+    jit = P.ColorJitter([2, 0, 3, 1], 1.13, 0.87, 1.19, -0.07)
+    lv0 = pyr(sets[0], flip)[0]
+    for _ in range(3):
+        jit(lv0)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        jit(lv0)
+    b.record()
+    torch.cuda.synchronize()
+    jit_ms = a.elapsed_time(b) / iters
     from PIL import Image
     t0 = time.perf_counter()
     n_cpu = 4
@@ -51,6 +63,7 @@ def main():
                       "algorithmic_MB": round(bytes_alg / 1e6, 2), "achieved_GBps": round(bytes_alg / (ms * 1e-3) / 1e9, 1),
                       "peak_GBps": peak, "roofline_frac": round(bytes_alg / (ms * 1e-3) / 1e9 / peak, 4),
                       "gpu_launches_per_batch": 1 + 2 * S,
+                      "color_jitter_level0_ms_per_batch": round(jit_ms, 4),
                       "pillow_host_ms_per_image_1_thread": round(cpu_ms_per_image, 2),
                       "pillow_host_ms_per_batch_1_thread": round(cpu_ms_per_image * N, 1)}))
 
