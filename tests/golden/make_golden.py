@@ -49,6 +49,7 @@ CASES = {
     "stereo_automask": (1, 32, 64, [0, -1, 1, "s"], True, "smooth", "row1_width", 2),
     "mono_nomask":     (1, 32, 64, [0, -1, 1], False, "smooth", "monodepth2", 3),
     "single_nomask":   (1, 32, 64, [0, 1], False, "smooth", "monodepth2", 4),
+    "five_frames":     (1, 32, 64, [0, -2, -1, 1, 2], True, "smooth", "monodepth2", 5),   # S = 4
 }
 
 
