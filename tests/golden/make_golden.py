@@ -50,6 +50,7 @@ CASES = {
     "mono_nomask":     (1, 32, 64, [0, -1, 1], False, "smooth", "monodepth2", 3),
     "single_nomask":   (1, 32, 64, [0, 1], False, "smooth", "monodepth2", 4),
     "five_frames":     (1, 32, 64, [0, -2, -1, 1, 2], True, "smooth", "monodepth2", 5),   # S = 4
+    "partial_tiles":   (2, 40, 72, [0, -1, 1], True, "smooth", "floor", 6),   # H, W not multiples of the 32x16 tile
 }
 
 

@@ -5,7 +5,8 @@ import numpy as np
 import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["mono_automask", "mono_iid", "stereo_automask", "mono_nomask", "single_nomask", "five_frames"]
+GOLDEN_CASES = ["mono_automask", "mono_iid", "stereo_automask", "mono_nomask", "single_nomask", "five_frames",
+                "partial_tiles"]
 
 
 def load_golden(name, device="cpu", dtype=torch.float32):
