@@ -131,11 +131,11 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_
     nets = MonoNets().to(device)
     if channels_last:   # NHWC activations for the cuDNN convolutions (precision-neutral); the loss inputs stay NCHW
         nets = nets.to(memory_format=torch.channels_last)
-    if ddp and graph:
-        # tried in round 1 (DDP built and warmed up on a side stream, 11 eager iterations, then capture): the
-        # capture never completed on this stack (torch 2.11 / NCCL 2.28.9, 2 GPUs) - single-GPU only for now
-        raise NotImplementedError("--graph is single-GPU only: capturing the DDP step hung in round 1")
-    model = nn.parallel.DistributedDataParallel(nets, device_ids=[device.index]) if ddp else nets
+    # With --graph the DDP wrapper is not used: capturing a DDP step never completed on this stack (torch 2.11 / NCCL
+    # 2.28.9, tried in round 1).  Instead the gradients live in one flat buffer, graph 1 replays forward + loss +
+    # backward, NCCL averages the flat buffer eagerly (one 111 MB all-reduce over NVLink), graph 2 replays Adam.
+    manual_ddp = ddp and graph
+    model = nn.parallel.DistributedDataParallel(nets, device_ids=[device.index]) if (ddp and not graph) else nets
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graph)
     batches = [synthetic_batch(B, H, W, frame_ids, s, device) for s in range(2)]
     if channels_last:
@@ -222,6 +222,58 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_
         return step, B
 
     static = {k: v.clone() for k, v in batches[0].items()}
+
+    if manual_ddp:
+        import torch.distributed as dist
+        params = [p for p in model.parameters()]
+        for p in params:   # identical initial weights on every rank (what the DDP constructor would do)
+            dist.broadcast(p.data, 0)
+        for b in model.buffers():
+            dist.broadcast(b.data, 0)
+        flat = torch.zeros(sum(p.numel() for p in params), device=device)
+        off = 0
+        for p in params:
+            # same strides as the parameter (channels-last conv weights): autograd's gradient layout contract
+            p.grad = flat[off:off + p.numel()].as_strided(p.size(), p.stride())
+            off += p.numel()
+
+        def fwd_bwd():
+            flat.zero_()
+            outputs = model(static, frame_ids)
+            loss = loss_fn(static, outputs)
+            loss.backward()          # accumulates into the views of `flat`
+            return loss
+
+        def full():
+            loss = fwd_bwd()
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            opt.step()
+            return loss
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                full()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            static_loss = fwd_bwd()
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            opt.step()
+
+        def graphed_ddp_step():
+            batch = batches[state["i"] % len(batches)]
+            state["i"] += 1
+            for k, v in batch.items():
+                static[k].copy_(v)
+            g1.replay()
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            g2.replay()
+            return static_loss
+
+        return graphed_ddp_step, B
 
     def body():
         outputs = model(static, frame_ids)
