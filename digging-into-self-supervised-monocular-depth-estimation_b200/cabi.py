@@ -48,7 +48,7 @@ class md2_grads(C.Structure):
 # every symbol include/md2_loss.h declares
 EXPORTS = ["md2_workspace_bytes", "md2_loss_forward", "md2_loss_forward_backward",
            "md2_loss_backward", "md2_pose_forward", "md2_pose_backward",
-           "md2_launches_per_step", "md2_version", "md2_debug_warp", "md2_set_tile_kernel_events",
+           "md2_launches_per_step", "md2_version", "md2_debug_warp", "md2_loss_forward_backward_timed",
            "md2_debug_div"]
 
 # include/md2_ops.h: the symbol-level operators (name -> argument types; all return int)
@@ -132,8 +132,10 @@ def load_library(path=None):
     lib.md2_launches_per_step.argtypes = [C.POINTER(md2_cfg), C.c_int]
     lib.md2_version.restype = C.c_char_p
     lib.md2_version.argtypes = []
-    lib.md2_set_tile_kernel_events.restype = None
-    lib.md2_set_tile_kernel_events.argtypes = [C.c_void_p, C.c_void_p]
+    lib.md2_loss_forward_backward_timed.restype = C.c_int
+    lib.md2_loss_forward_backward_timed.argtypes = [C.POINTER(md2_cfg), C.POINTER(md2_inputs),
+                                                    C.POINTER(md2_outputs), C.POINTER(md2_grads), C.c_float,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.md2_debug_div.restype = C.c_int
     lib.md2_debug_div.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.md2_debug_warp.restype = C.c_int
@@ -265,7 +267,8 @@ class CLoss:
             raise RuntimeError(f"md2_loss_forward returned {rc}")
         return o
 
-    def forward_backward(self, args, grad_loss=1.0):
+    def forward_backward(self, args, grad_loss=1.0, events=None):
+        """events = (start, stop) torch.cuda.Event pair (already recorded once): timed around the tile kernel."""
         import torch
         a, cfg, inp = self._prep(args)
         dev = a["target"].device
@@ -275,8 +278,13 @@ class CLoss:
         gT = [torch.full((cfg.B, 4, 4), float("nan"), device=dev) for _ in a["Ts"]]
         out = make_outputs(o["loss"], o["per_pixel"], o["argmin"], o["depth"])
         g = make_grads(gd, gT)
-        rc = self.lib.md2_loss_forward_backward(C.byref(cfg), C.byref(inp), C.byref(out), C.byref(g),
-                                                C.c_float(grad_loss), C.c_void_p(ws.data_ptr()), self._stream())
+        if events is not None:
+            rc = self.lib.md2_loss_forward_backward_timed(
+                C.byref(cfg), C.byref(inp), C.byref(out), C.byref(g), C.c_float(grad_loss), C.c_void_p(ws.data_ptr()),
+                self._stream(), C.c_void_p(events[0].cuda_event), C.c_void_p(events[1].cuda_event))
+        else:
+            rc = self.lib.md2_loss_forward_backward(C.byref(cfg), C.byref(inp), C.byref(out), C.byref(g),
+                                                    C.c_float(grad_loss), C.c_void_p(ws.data_ptr()), self._stream())
         if rc != 0:
             raise RuntimeError(f"md2_loss_forward_backward returned {rc}")
         o["grad_disp"], o["grad_T"] = gd, gT

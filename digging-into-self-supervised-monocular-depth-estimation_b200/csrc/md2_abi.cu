@@ -31,17 +31,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static EncodeTiledFn lookup_encode_tiled() {
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+      q == cudaDriverEntryPointSuccess)
+    return (EncodeTiledFn)ptr;
+  return nullptr;
+}
 static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
+  static const EncodeTiledFn fn = lookup_encode_tiled();  // function-local static: initialised once, thread-safe
   return fn;
 }
 
@@ -126,20 +125,19 @@ __global__ void __launch_bounds__(TK::NT, TK::BWD ? MD2_MINB : 1)
   TK::prologue_windows(c, tid);
   __syncthreads();
   for (int s = 0; s < p.ns; ++s) {
+    if (TK::BWD && s > 0) TK::phase_d2(c, s - 1, tid);  // column pass of the previous scale's upsample adjoint
     TK::template phase_a<DBG>(c, s, tid);
     __syncthreads();
     TK::phase_b(c, s, tid, regs);
     __syncthreads();
     if (TK::BWD) {
       TK::phase_c(c, s, tid, regs);
-      __syncthreads();
+      __syncwarp();  // phase D1 reads the two tile rows its own warp has just produced
       TK::phase_d1(c, s, tid);
-      if (s > 0) {  // scale 0 has no second pass
-        __syncthreads();
-        TK::phase_d2(c, s, tid);
-      }
+      __syncthreads();
     }
   }
+  if (TK::BWD) TK::phase_d2(c, p.ns - 1, tid);
   TK::epilogue1(c, tid, regs);
   __syncthreads();
   TK::epilogue2(c, tid);
@@ -282,52 +280,79 @@ __global__ void debug_div_kernel(int n, const float* num, const float* den, floa
   }
 }
 
-static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
-static bool g_tma_enabled = true;   // MD2_NO_TMA=1 in the environment disables the TMA path (A/B measurement)
-static bool g_side_enabled = true;  // MD2_NO_SIDE=1 keeps the smoothness kernels on the caller's stream
+// environment switches for A/B measurements, read once (thread-safe function-local statics)
+static bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
+static bool tma_enabled() {   // MD2_NO_TMA=1 disables the TMA path
+  static const bool v = !env_flag("MD2_NO_TMA");
+  return v;
+}
+static bool side_enabled() {  // MD2_NO_SIDE=1 keeps the smoothness kernels on the caller's stream
+  static const bool v = !env_flag("MD2_NO_SIDE");
+  return v;
+}
+
+// per-call measurement hook (md2_loss_forward_backward_timed): events recorded around the tile kernel
+struct TileEvents {
+  cudaEvent_t start, stop;
+};
+
+constexpr int kMaxDevices = 64;
+
+// occupancy experiments only (tools/variants.py): extra dynamic shared memory per CTA
+#ifndef MD2_EXTRA_SMEM
+#define MD2_EXTRA_SMEM 0
+#endif
 
 template <class TK, bool DBG>
-static cudaError_t launch_tiles_impl(const Params& p, cudaStream_t st) {
-  static bool attr_set = false;  // per instantiation; the attribute is sticky for the process
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tile_kernel<TK, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)TK::SMEM_BYTES);
+static cudaError_t launch_tiles_impl(const Params& p, cudaStream_t st, const TileEvents* ev) {
+  // The dynamic shared-memory limit is a per-device (per-context) function attribute: set it once per device.
+  // A racing second thread only repeats the (idempotent) call.
+  static bool attr_set[kMaxDevices] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(tile_kernel<TK, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)TK::SMEM_BYTES + MD2_EXTRA_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
   }
   const dim3 grid(p.tiles_x, p.tiles_y, p.B);
   // TMA staging of the target / raw source tiles when the layout allows it (16-byte aligned bases, W % 4 == 0,
   // box row a multiple of 16 bytes); otherwise the kernel loads the tiles with plain coalesced loads
   TmaMaps maps;
   Params q = p;
-  q.use_tma = g_tma_enabled && (TK::TW % 4 == 0) && make_image_map(&maps.target, p.target, p.B, p.H, p.W, TK::R2P, TK::R2H);
-  if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
-  tile_kernel<TK, DBG><<<grid, TK::NT, TK::SMEM_BYTES, st>>>(q, maps);
-  if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
+  q.use_tma = tma_enabled() && (TK::TW % 4 == 0) && make_image_map(&maps.target, p.target, p.B, p.H, p.W, TK::R2P, TK::R2H);
+  if (ev) cudaEventRecord(ev->start, st);
+  tile_kernel<TK, DBG><<<grid, TK::NT, TK::SMEM_BYTES + MD2_EXTRA_SMEM, st>>>(q, maps);
+  if (ev) cudaEventRecord(ev->stop, st);
   return cudaGetLastError();
 }
 
 template <class TK>
-static cudaError_t launch_tiles(const Params& p, cudaStream_t st) {
-  if (!TK::BWD && p.dbg_coords) return launch_tiles_impl<TK, !TK::BWD>(p, st);  // debug tap: forward build only
-  return launch_tiles_impl<TK, false>(p, st);
+static cudaError_t launch_tiles(const Params& p, cudaStream_t st, const TileEvents* ev) {
+  if (!TK::BWD && p.dbg_coords) return launch_tiles_impl<TK, !TK::BWD>(p, st, ev);  // debug tap: forward build only
+  return launch_tiles_impl<TK, false>(p, st, ev);
 }
 
 template <bool BWD, int MM>
-static cudaError_t dispatch_tiles_s(const Params& p, cudaStream_t st) {
+static cudaError_t dispatch_tiles_s(const Params& p, cudaStream_t st, const TileEvents* ev) {
   switch (p.S) {
-    case 1: return launch_tiles<Tile<1, BWD, kTW, tile_h(1), tile_nt(1, BWD), MM>>(p, st);
-    case 2: return launch_tiles<Tile<2, BWD, kTW, tile_h(2), tile_nt(2, BWD), MM>>(p, st);
-    case 3: return launch_tiles<Tile<3, BWD, kTW, tile_h(3), tile_nt(3, BWD), MM>>(p, st);
-    default: return launch_tiles<Tile<4, BWD, kTW, tile_h(4), tile_nt(4, BWD), MM>>(p, st);
+    case 1: return launch_tiles<Tile<1, BWD, kTW, tile_h(1), tile_nt(1, BWD), MM>>(p, st, ev);
+    case 2: return launch_tiles<Tile<2, BWD, kTW, tile_h(2), tile_nt(2, BWD), MM>>(p, st, ev);
+    case 3: return launch_tiles<Tile<3, BWD, kTW, tile_h(3), tile_nt(3, BWD), MM>>(p, st, ev);
+    default: return launch_tiles<Tile<4, BWD, kTW, tile_h(4), tile_nt(4, BWD), MM>>(p, st, ev);
   }
 }
 template <bool BWD>
-static cudaError_t dispatch_tiles(const Params& p, cudaStream_t st) {
+static cudaError_t dispatch_tiles(const Params& p, cudaStream_t st, const TileEvents* ev) {
   switch (matmul_mode(p.B, p.H, p.W)) {
-    case 0: return dispatch_tiles_s<BWD, 0>(p, st);
-    case 1: return dispatch_tiles_s<BWD, 1>(p, st);
-    default: return dispatch_tiles_s<BWD, 2>(p, st);
+    case 0: return dispatch_tiles_s<BWD, 0>(p, st, ev);
+    case 1: return dispatch_tiles_s<BWD, 1>(p, st, ev);
+    default: return dispatch_tiles_s<BWD, 2>(p, st, ev);
   }
 }
 
@@ -337,34 +362,30 @@ struct SideStream {
   cudaEvent_t fork, join;
 };
 static SideStream* side_stream() {
-  thread_local SideStream cache[16];
-  thread_local bool ready[16] = {false};
+  thread_local SideStream cache[kMaxDevices];
+  thread_local bool ready[kMaxDevices] = {false};
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
   if (!ready[dev]) {
-    if (cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&cache[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&cache[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    SideStream s = {nullptr, nullptr, nullptr};
+    const bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {  // release whatever was created: the next call starts from scratch
+      if (s.join) cudaEventDestroy(s.join);
+      if (s.fork) cudaEventDestroy(s.fork);
+      if (s.stream) cudaStreamDestroy(s.stream);
+      return nullptr;
+    }
+    cache[dev] = s;
     ready[dev] = true;
   }
   return &cache[dev];
 }
 
-static void read_env_once() {
-  static bool done = false;
-  if (!done) {
-    done = true;
-    const char* e = getenv("MD2_NO_TMA");
-    if (e && e[0] == '1') g_tma_enabled = false;
-    e = getenv("MD2_NO_SIDE");
-    if (e && e[0] == '1') g_side_enabled = false;
-  }
-}
-
 static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out, const md2_grads* g,
                     float grad_loss, const float* grad_loss_dev, const uint8_t* saved_k, void* workspace,
-                    md2_stream_t stream, Mode mode, const Params* tweak) {
-  read_env_once();
+                    md2_stream_t stream, Mode mode, const Params* tweak, const TileEvents* ev = nullptr) {
   int e = validate_cfg(cfg);
   if (e) return e;
   e = validate_inputs(cfg, in);
@@ -398,8 +419,9 @@ static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs*
     zero_grads_kernel<<<296, 256, 0, st>>>(p);
     if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
   }
-  cudaStream_t ss = g_side_enabled ? side->stream : st;
-  if (g_side_enabled) {
+  const bool use_side = side_enabled();
+  cudaStream_t ss = use_side ? side->stream : st;
+  if (use_side) {
     if ((ce = cudaEventRecord(side->fork, st)) != cudaSuccess) return (int)ce;
     if ((ce = cudaStreamWaitEvent(ss, side->fork, 0)) != cudaSuccess) return (int)ce;
   }
@@ -409,10 +431,10 @@ static int run_step(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs*
     smooth_backward_kernel<<<p.B * smooth_total(p.ns), 256, 0, ss>>>(p);
     if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
   }
-  if (g_side_enabled && (ce = cudaEventRecord(side->join, ss)) != cudaSuccess) return (int)ce;
-  ce = mode == kForward ? dispatch_tiles<false>(p, st) : dispatch_tiles<true>(p, st);
+  if (use_side && (ce = cudaEventRecord(side->join, ss)) != cudaSuccess) return (int)ce;
+  ce = mode == kForward ? dispatch_tiles<false>(p, st, ev) : dispatch_tiles<true>(p, st, ev);
   if (ce != cudaSuccess) return (int)ce;
-  if (g_side_enabled && (ce = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return (int)ce;
+  if (use_side && (ce = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return (int)ce;
   GradTPtrs gT;
   for (int f = 0; f < kMaxS; ++f) gT.p[f] = (g && f < cfg->S) ? g->grad_T[f] : nullptr;
   finalize_kernel<<<1 + (mode != kForward ? p.B * p.S : 0), kFinNT, 0, st>>>(p, mode == kBackward ? nullptr : out->loss, gT,
@@ -499,9 +521,12 @@ int md2_debug_div(int n, const float* num, const float* den, float* q_div, float
   return ce == cudaSuccess ? 0 : (int)ce;
 }
 
-void md2_set_tile_kernel_events(void* start_event, void* stop_event) {
-  md2::g_ev_start = (cudaEvent_t)start_event;
-  md2::g_ev_stop = (cudaEvent_t)stop_event;
+int md2_loss_forward_backward_timed(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out,
+                                    const md2_grads* grads, float grad_loss, void* workspace, md2_stream_t stream,
+                                    void* start_event, void* stop_event) {
+  if (!start_event || !stop_event) return MD2_ERR_NULL;
+  const TileEvents ev = {(cudaEvent_t)start_event, (cudaEvent_t)stop_event};
+  return run_step(cfg, in, out, grads, grad_loss, nullptr, nullptr, workspace, stream, kFused, nullptr, &ev);
 }
 
 const char* md2_version(void) { return "md2loss 0.1 sm_100a"; }

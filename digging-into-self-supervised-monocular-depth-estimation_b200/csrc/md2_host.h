@@ -34,7 +34,10 @@ constexpr int tile_h(int S) { return S <= 2 ? kTH : (S == 3 ? (kTH * 3) / 4 : kT
 // Threads per CTA: with the backward, 10 warps measured 1.3 % faster than 8 for the 32x16 tile (0.750 vs
 // 0.761 ms); the forward-only build is much slower with 10 (584 vs 421 us under ncu: it no longer fits
 // three CTAs per SM) and the smaller tiles of S >= 3 keep 8.
-constexpr int tile_nt(int S, bool bwd) { return (bwd && S <= 2 && kNT == 256) ? 320 : kNT; }
+#ifndef MD2_NT_BWD
+#define MD2_NT_BWD 320
+#endif
+constexpr int tile_nt(int S, bool bwd) { return (bwd && S <= 2) ? MD2_NT_BWD : kNT; }
 
 enum Mode { kForward = 0, kFused = 1, kBackward = 2 };
 
@@ -118,6 +121,7 @@ inline void fill_params(Params& p, const md2_cfg* c, const md2_inputs* in, const
     if (g) p.grad_disp[s] = g->grad_disp[s];
   }
   p.K = in->K; p.invK = in->inv_K; p.seed = in->seed;
+  mix_seed(in->seed, p.seed_m1, p.seed_m2);
   if (out) { p.per_px = out->per_pixel; p.argmin = out->argmin; p.depth = out->depth; }
   const Workspace w = workspace_layout(c);
   char* ws = (char*)workspace;
@@ -126,6 +130,8 @@ inline void fill_params(Params& p, const md2_cfg* c, const md2_inputs* in, const
   p.smooth_part = (float*)(ws + w.off_smooth);
   p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y; p.n_tiles = w.n_tiles;
   p.gcoef = (float)(1.0 / ((double)c->num_scales * c->B * c->H * c->W));
+  // scale-0 gradients leave the tile as 16-byte vector reductions when the rows allow it
+  p.vec_atomics = (g && g->grad_disp[0] && ((uintptr_t)g->grad_disp[0] & 15) == 0 && (c->W & 3) == 0) ? 1 : 0;
   p.grad_loss_host = 1.0f;
   p.dbg_scale = -1; p.dbg_source = -1;
 }

@@ -35,7 +35,17 @@ MD2_FN float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 MD2_FN float frcp(float a) { return __frcp_rn(a); }
 MD2_FN float ld_ro(const float* p) { return __ldg(p); }
 MD2_FN uint8_t ld_ro(const uint8_t* p) { return __ldg(p); }
+// Keeps a computed address in a register pair: without it nvcc carries 64-bit element offsets and rebuilds the byte
+// address (LEA + LEA.HI.X) for every load of a gather footprint.
+MD2_FN const float* opaque_ptr(const float* p) {
+  asm("" : "+l"(p));
+  return p;
+}
 MD2_FN void atomic_add(float* p, float v) { atomicAdd(p, v); }
+// one 16-byte reduction (red.global.add.v4.f32, sm_90+) for four consecutive floats; p is 16-byte aligned
+MD2_FN void atomic_add4(float* p, const float* v) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
 #else
 MD2_FN float fadd(float a, float b) { return a + b; }
 MD2_FN float fsub(float a, float b) { return a - b; }
@@ -45,7 +55,9 @@ MD2_FN float fdiv(float a, float b) { return a / b; }
 MD2_FN float frcp(float a) { return 1.0f / a; }
 MD2_FN float ld_ro(const float* p) { return *p; }
 MD2_FN uint8_t ld_ro(const uint8_t* p) { return *p; }
+MD2_FN const float* opaque_ptr(const float* p) { return p; }
 MD2_FN void atomic_add(float* p, float v) { *p += v; }
+MD2_FN void atomic_add4(float* p, const float* v) { for (int i = 0; i < 4; ++i) p[i] += v[i]; }
 #endif
 
 // ---- packed pairs: two independent fp32 lanes per instruction (add/mul/fma.rn.f32x2 on sm_100) ----

@@ -116,10 +116,12 @@ int md2_pose_backward(int n, const float* axisangle, const float* translation, i
 int md2_launches_per_step(const md2_cfg* cfg, int with_backward);
 const char* md2_version(void);
 
-/* Measurement hook for bench.py: when both are non-NULL, every following step call records
- * `start` / `stop` (cudaEvent_t) on its stream immediately around the tile kernel - the
- * dominant launch - so its duration can be read without a profiler.  NULL, NULL disables. */
-void md2_set_tile_kernel_events(void* start_event, void* stop_event);
+/* md2_loss_forward_backward with a per-call measurement hook (bench.py's roofline leg): records the two
+ * caller-owned cudaEvent_t `start_event` / `stop_event` on `stream` immediately around the tile kernel - the
+ * dominant launch - so that its duration can be read without a profiler.  No process-global state. */
+int md2_loss_forward_backward_timed(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out,
+                                    const md2_grads* grads, float grad_loss, void* workspace,
+                                    md2_stream_t stream, void* start_event, void* stop_event);
 
 /* Debug taps used by the parity tests only: the sampling coordinates (ix, iy) in pixels
  * after un-normalisation and before clipping, and the warped image, for source f at

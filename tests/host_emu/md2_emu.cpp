@@ -35,14 +35,15 @@ static void run_tiles(const Params& p) {
     }
     PHASE(TK::prologue_windows(c, tid));
     for (int s = 0; s < p.ns; ++s) {
+      if (TK::BWD && s > 0) PHASE(TK::phase_d2(c, s - 1, tid));
       PHASE(TK::template phase_a<true>(c, s, tid));
       PHASE(TK::phase_b(c, s, tid, regs[tid]));
       if (TK::BWD) {
         PHASE(TK::phase_c(c, s, tid, regs[tid]));
         PHASE(TK::phase_d1(c, s, tid));
-        PHASE(TK::phase_d2(c, s, tid));
       }
     }
+    if (TK::BWD) PHASE(TK::phase_d2(c, p.ns - 1, tid));
     PHASE(TK::epilogue1(c, tid, regs[tid]));
     PHASE(TK::epilogue2(c, tid));
   }

@@ -15,10 +15,9 @@ out = cl.forward_backward(a)
 torch.cuda.synchronize()
 k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 k0.record(); k1.record(); torch.cuda.synchronize()
-cl.lib.md2_set_tile_kernel_events(C.c_void_p(k0.cuda_event), C.c_void_p(k1.cuda_event))
 ts = []
 for i in range(12):
-    cl.forward_backward(a); torch.cuda.synchronize(); ts.append(k0.elapsed_time(k1))
+    cl.forward_backward(a, events=(k0, k1)); torch.cuda.synchronize(); ts.append(k0.elapsed_time(k1))
 ts = sorted(ts[2:])
 print(json.dumps({"lib": os.path.basename(os.environ["MD2_LIB"]), "kernel_ms_med": ts[len(ts)//2], "kernel_ms_min": ts[0],
                   "loss": float(out["loss"]), "gsum": float(out["grad_disp"][0].double().abs().sum())}))
