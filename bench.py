@@ -40,6 +40,9 @@ import torch  # noqa: E402
 
 B, H, W, FRAME_IDS, NUM_SCALES = 12, 192, 640, [0, -1, 1], 4
 S = len(FRAME_IDS) - 1
+# "iid": every disparity value is an independent U(0,1) draw, i.e. neighbouring pixels sample the source frames up to
+# 37 pixels apart (the worst case for the gather); "smooth": band-limited disparities like a network's
+DISP_KIND = os.environ.get("MD2_BENCH_DISP", "iid")
 METRIC = "warped_pixels_per_sec_fused_loss_fwd_bwd"
 UNIT = "warped_px/s"
 WORKLOAD = "fused view-synthesis loss fwd+bwd, batch 12 per GPU, 192x640, frame_ids [0,-1,1], 4 scales, automask, fp32"
@@ -144,6 +147,11 @@ def make_host_batch(seed):
     import md2_b200.synthetic as syn
     from oracle.oracle_torch import pose_matrix  # only to build pose matrices for the synthetic batch
     inputs, outputs = syn.make_batch(B, H, W, FRAME_IDS, NUM_SCALES, seed, "iid", requires_grad=False)
+    if DISP_KIND == "smooth":
+        # network-like disparities: band-limited fields instead of i.i.d. values (see config["gather"])
+        smooth = syn.make_batch(B, H, W, FRAME_IDS, NUM_SCALES, seed, "smooth", requires_grad=False)[1]
+        for s in range(NUM_SCALES):
+            outputs[("disp", s)] = smooth[("disp", s)]
     for f in FRAME_IDS[1:]:
         outputs[("c2c", f, 0)] = pose_matrix(outputs[("axisangle", f)], outputs[("translation", f)],
                                              invert=(f < 0)).detach()

@@ -17,6 +17,11 @@
 
 #include "md2_host.h"
 
+// phase-skipping experiments only (tools/variants.py): bit 0 phase A, 1 phase B, 2 phase C, 3 phase D
+#ifndef MD2_SKIP
+#define MD2_SKIP 0
+#endif
+
 namespace md2 {
 
 // ---------------------------------------------------------------------------------------- TMA
@@ -101,8 +106,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 }
 
 // grid (tiles_x, tiles_y, B): one CTA per image tile
+// register budget: MD2_MINB CTAs of the training build per SM (64 K registers, allocated in units of 8 per thread)
+template <class TK>
+constexpr int tile_max_regs() {
+  const int r = TK::BWD ? (65536 / (MD2_MINB * TK::NT)) / 8 * 8 : 255;
+  return r > 255 ? 255 : r;
+}
 template <class TK, bool DBG>
-__global__ void __launch_bounds__(TK::NT, TK::BWD ? MD2_MINB : 1)
+__global__ void __launch_bounds__(TK::NT) __maxnreg__(tile_max_regs<TK>())
     tile_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps maps) {
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x;
@@ -125,19 +136,19 @@ __global__ void __launch_bounds__(TK::NT, TK::BWD ? MD2_MINB : 1)
   TK::prologue_windows(c, tid);
   __syncthreads();
   for (int s = 0; s < p.ns; ++s) {
-    if (TK::BWD && s > 0) TK::phase_d2(c, s - 1, tid);  // column pass of the previous scale's upsample adjoint
-    TK::template phase_a<DBG>(c, s, tid);
+    if (TK::BWD && s > 0 && !(MD2_SKIP & 8)) TK::phase_d2(c, s - 1, tid);  // column pass of the previous scale's upsample adjoint
+    if (!(MD2_SKIP & 1)) TK::template phase_a<DBG>(c, s, tid);
     __syncthreads();
-    TK::phase_b(c, s, tid, regs);
+    if (!(MD2_SKIP & 2)) TK::phase_b(c, s, tid, regs);
     __syncthreads();
     if (TK::BWD) {
-      TK::phase_c(c, s, tid, regs);
+      if (!(MD2_SKIP & 4)) TK::phase_c(c, s, tid, regs);
       __syncwarp();  // phase D1 reads the two tile rows its own warp has just produced
-      TK::phase_d1(c, s, tid);
+      if (!(MD2_SKIP & 8)) TK::phase_d1(c, s, tid);
       __syncthreads();
     }
   }
-  if (TK::BWD) TK::phase_d2(c, p.ns - 1, tid);
+  if (TK::BWD && !(MD2_SKIP & 8)) TK::phase_d2(c, p.ns - 1, tid);
   TK::epilogue1(c, tid, regs);
   __syncthreads();
   TK::epilogue2(c, tid);

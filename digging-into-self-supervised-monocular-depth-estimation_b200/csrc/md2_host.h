@@ -28,16 +28,27 @@ namespace md2 {
 constexpr int kTW = MD2_TW;
 constexpr int kTH = MD2_TH;
 constexpr int kNT = MD2_NT;
-// Tile height per source count: the backward build keeps S-proportional buffers in shared memory, so the
-// tile shrinks with S to keep two CTAs resident per SM (<= ~113 KB each).
-constexpr int tile_h(int S) { return S <= 2 ? kTH : (S == 3 ? (kTH * 3) / 4 : kTH / 2); }
-// Threads per CTA: with the backward, 10 warps measured 1.3 % faster than 8 for the 32x16 tile (0.750 vs
-// 0.761 ms); the forward-only build is much slower with 10 (584 vs 421 us under ncu: it no longer fits
-// three CTAs per SM) and the smaller tiles of S >= 3 keep 8.
+// Tile height per source count: the backward build keeps S-proportional buffers in shared memory, so the tile
+// shrinks with S to keep two CTAs resident per SM (<= ~113 KB each; DESIGN.md 4 lists the sizes).
+#ifndef MD2_TH3
+#define MD2_TH3 12
+#endif
+#ifndef MD2_TH4
+#define MD2_TH4 12
+#endif
+constexpr int tile_h(int S) { return S <= 2 ? kTH : (S == 3 ? MD2_TH3 : MD2_TH4); }
+// Threads per CTA of the training build, chosen so that the cells of phase A (36 x (TH+4)), the two-window runs of
+// phase B (34 x (TH+2)/2) and the pixel runs of phase C (32 x TH/2) fill whole passes: 320 threads for the 32x16
+// tile (720 cells / 306 runs / 256 runs); the 32x12 tile of S >= 3 (576 / 238 / 192) needs 128 registers per thread
+// for its two units and keeps 256 (288 threads at 112 registers spill: 1.83 vs 1.16 ms at S = 3).  The forward-only
+// build has 32 x TH/2 runs and uses kNT.
 #ifndef MD2_NT_BWD
 #define MD2_NT_BWD 320
 #endif
-constexpr int tile_nt(int S, bool bwd) { return (bwd && S <= 2) ? MD2_NT_BWD : kNT; }
+#ifndef MD2_NT_BWD34
+#define MD2_NT_BWD34 256
+#endif
+constexpr int tile_nt(int S, bool bwd) { return !bwd ? kNT : (S <= 2 ? MD2_NT_BWD : MD2_NT_BWD34); }
 
 enum Mode { kForward = 0, kFused = 1, kBackward = 2 };
 

@@ -14,6 +14,8 @@ cl = cabi.CLoss()
 FR = {1: [0, 1], 2: [0, -1, 1], 3: [0, -1, 1, "s"], 4: [0, -1, 1, "s", 2]}
 cases = [(12, h, w, s) for (h, w) in ((96, 320), (192, 640), (288, 960), (320, 1024), (384, 1280)) for s in (1, 2, 3, 4)]
 cases.append((8, 320, 1024, 3))  # configs[3]: mono+stereo high-res, per-GPU batch 8
+if os.environ.get("MD2_SWEEP_CASES"):  # "B,H,W,S;B,H,W,S;..." for quick A/B runs
+    cases = [tuple(int(x) for x in c.split(",")) for c in os.environ["MD2_SWEEP_CASES"].split(";")]
 rows = []
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for B, H, W, S in cases:
