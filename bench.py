@@ -21,9 +21,13 @@ A step is one pass of the hot path over one batch:
            bytes N*(183.8125 + 112*S) against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the oracle port of the reference's PyTorch path on the host cores, bounded sample.
 
---impl reference times that CPU port (oracle/oracle_torch.py) as the reference arm: the reference is
-Python and cannot travel to the GPU box (it is not copied into this repo); the port is pinned to the
-reference's own outputs by tests/test_oracle_golden.py.
+  gpu_reference  the reference's own loss step (oracle/_ref when staged, else the port) on the SAME GPU at the
+           same configuration, forward + backward, CUDA-event timed: as shipped (host torch.randn + H2D per scale,
+           processor.py:195) and with the noise drawn on the device (SURVEY.md 8d ii).
+
+--impl reference times the reference's CPU implementation of the path on the host cores: the unmodified
+reference staged by oracle/stage_ref.py into the git-ignored oracle/_ref/ (it travels to the GPU box like a built
+.so), else the port oracle/oracle_torch.py, which is pinned to the reference's outputs by tests/test_oracle_golden.py.
 """
 import argparse
 import json
@@ -50,6 +54,70 @@ WORKLOAD = "fused view-synthesis loss fwd+bwd, batch 12 per GPU, 192x640, frame_
 
 def algorithmic_bytes(b, h, w, s):
     return b * h * w * (183.8125 + 112.0 * s)
+
+
+def cross_scale_bytes(b, h, w, s):
+    """SURVEY.md 8d cross-scale lower bound (every distinct input read once per pass for all four scales, the loss
+    reduced in-kernel, only depth(0,0) written): 17.5 bytes per warped pixel, 206 MB at batch 12, 192x640, S=2."""
+    return 17.5 * b * s * NUM_SCALES * h * w
+
+
+def gpu_reference(dev, ours_ms):
+    """The reference's loss step on this GPU at the benchmark configuration (SURVEY.md 8d ii), forward + backward,
+    CUDA events, median of 20 after 3 warm-up steps: as shipped and with the auto-mask noise drawn on the device."""
+    sys.path.insert(0, ROOT)
+    res = {}
+    try:
+        from oracle import ref_loader as RL
+        if RL.available():
+            mk = lambda host_noise: RL.make_step(B, H, W, FRAME_IDS, dev, NUM_SCALES, 0, "iid", host_noise)
+            res["kind"] = "reference (oracle/_ref: model_tool/processor.py image2warping + compute_loss + backward)"
+        else:
+            raise RuntimeError("not staged")
+    except Exception:
+        from oracle import oracle_torch as O
+        import md2_b200.synthetic as syn
+        inputs, outputs = syn.make_batch(B, H, W, FRAME_IDS, NUM_SCALES, 0, "iid", requires_grad=False)
+        g = lambda t: t.to(dev)
+        srcs = FRAME_IDS[1:]
+        Ts = [O.pose_matrix(g(outputs[("axisangle", f)]), g(outputs[("translation", f)]), invert=(f < 0)).detach()
+              for f in srcs]
+        base = dict(target=g(inputs[("color", 0, 0)]), sources=[g(inputs[("color", f, 0)]) for f in srcs],
+                    color_pyr=[g(inputs[("color", 0, s)]) for s in range(NUM_SCALES)], K=g(inputs[("K", 0)]),
+                    inv_K=g(inputs[("inv_K", 0)]), automask=True)
+        disp0 = [g(outputs[("disp", s)]) for s in range(NUM_SCALES)]
+
+        def mk(host_noise):
+            def step():
+                disps = [d.clone().requires_grad_(True) for d in disp0]
+                T = [t.clone().requires_grad_(True) for t in Ts]
+                nz = None if host_noise else [torch.randn(B, S, H, W, device=dev) for _ in range(NUM_SCALES)]
+                out = O.view_synthesis_loss(disps=disps, Ts=T, noise=nz, **base)
+                out["loss"].backward()
+                return out["loss"].detach()
+            return step
+        res["kind"] = "port (oracle/oracle_torch.py on cuda)"
+
+    def timed(step, n=20):
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2], ts[0]
+    a_med, a_min = timed(mk(True))
+    b_med, b_min = timed(mk(False))
+    res.update({"ms_as_shipped": a_med, "ms_as_shipped_min": a_min, "ms_noise_on_device": b_med,
+                "ms_noise_on_device_min": b_min, "ours_ms_per_step": ours_ms,
+                "config": "batch 12, 192x640, frame_ids [0,-1,1], 4 scales, fp32, same GPU, eager PyTorch ops"})
+    return res
 
 
 def hbm_peak():
@@ -142,10 +210,12 @@ def ncu_traffic():
         return None, None
 
 
-def make_host_batch(seed):
-    """One synthetic batch on the host, shaped like the reference loaders' output."""
+def make_host_batch(seed, dev="cuda"):
+    """One synthetic batch on the host, shaped like the reference loaders' output (pose matrices from this
+    package's own param2matrix kernel)."""
     import md2_b200.synthetic as syn
-    from oracle.oracle_torch import pose_matrix  # only to build pose matrices for the synthetic batch
+    from md2_b200.functional import param2matrix
+    pose_matrix = lambda a, t, invert: param2matrix(a.to(dev), t.to(dev), invert).cpu()
     inputs, outputs = syn.make_batch(B, H, W, FRAME_IDS, NUM_SCALES, seed, "iid", requires_grad=False)
     if DISP_KIND == "smooth":
         # network-like disparities: band-limited fields instead of i.i.d. values (see config["gather"])
@@ -195,7 +265,7 @@ def run_ours(args):
     lib = cl.lib
     # ---- device-resident leg: rotating sets larger than L2 -------------------------------------
     n_sets = 3
-    host = [make_host_batch(100 * rank + i) for i in range(n_sets)]
+    host = [make_host_batch(100 * rank + i, dev) for i in range(n_sets)]
     sets = []
     set_bytes = 0
     for inputs, outputs in host:
@@ -363,6 +433,12 @@ def run_ours(args):
     achieved = algo / (kernel_ms * 1e-3) / 1e9
 
     traffic, traffic_src = ncu_traffic()
+    # bytes the timed launch really moves (no per-pixel loss map written, no noise tensor read: bench passes neither)
+    # and the cross-scale lower bound (every distinct input once per step)
+    n_px = B * H * W
+    algo_matched = algo - NUM_SCALES * n_px * (4 + 4 * S)
+    algo_cross = cross_scale_bytes(B, H, W, S)
+    gpu_ref = gpu_reference(dev, ms_total / args.steps) if rank == 0 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -384,8 +460,20 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": "md2::tile_kernel<Tile<2,true,32,16,320>>",
-                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo, "peak_source": peak_src},
+                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
+                     "frac_matched": algo_matched / (kernel_ms * 1e-3) / 1e9 / peak,
+                     "matched_bytes_per_launch": algo_matched,
+                     "frac_cross_scale": algo_cross / (kernel_ms * 1e-3) / 1e9 / peak,
+                     "cross_scale_bytes_per_launch": algo_cross,
+                     "note": "frac uses SURVEY 8d's per-scale bytes (601 MB); frac_matched drops the per-pixel loss "
+                             "write and the noise read this call does not perform; frac_cross_scale counts every "
+                             "distinct input once per step"},
     }
+    if gpu_ref is not None:
+        line["gpu_reference"] = gpu_ref
+        line["speedup_vs_gpu_reference"] = {
+            "as_shipped_host_randn": gpu_ref["ms_as_shipped"] / (ms_total / args.steps),
+            "noise_on_device": gpu_ref["ms_noise_on_device"] / (ms_total / args.steps)}
     if rank == 0:
         line["cpu_baseline"] = cpu_baseline(steps=3)
         print(json.dumps(line), flush=True)
@@ -393,15 +481,23 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# ------------------------------------------------------------------------------------ CPU port
-CPU_B = 4  # bounded sample: one third of the batch (same image size, sources and scales)
+# ------------------------------------------------------------------------------------ CPU reference
+CPU_B = 4  # cpu_baseline of the ours arm: bounded sample, one third of the batch (same image size, sources, scales)
 
 
-def cpu_step_fn():
+def cpu_step_fn(batch):
+    """-> (step, kind).  The reference's own code from oracle/_ref when it is staged, else the port."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    try:
+        from oracle import ref_loader as RL
+        if RL.available():
+            step = RL.make_step(batch, H, W, FRAME_IDS, "cpu", NUM_SCALES, 0, "iid", True)
+            return (lambda: float(step())), "reference"
+    except Exception:
+        pass
     from oracle import oracle_torch as O
     import md2_b200.synthetic as syn
-    torch.set_num_threads(os.cpu_count() or 1)
-    inputs, outputs = syn.make_batch(CPU_B, H, W, FRAME_IDS, NUM_SCALES, 0, "iid", requires_grad=False)
+    inputs, outputs = syn.make_batch(batch, H, W, FRAME_IDS, NUM_SCALES, 0, "iid", requires_grad=False)
     srcs = FRAME_IDS[1:]
     Ts = [O.pose_matrix(outputs[("axisangle", f)], outputs[("translation", f)], invert=(f < 0)).detach()
           for f in srcs]
@@ -415,44 +511,47 @@ def cpu_step_fn():
         out = O.view_synthesis_loss(disps=disps, Ts=T, **base)
         out["loss"].backward()
         return float(out["loss"].detach())
-    return step
+    return step, "port"
 
 
 def cpu_baseline(steps=3):
-    step = cpu_step_fn()
+    step, kind = cpu_step_fn(CPU_B)
     step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
     px = CPU_B * S * NUM_SCALES * H * W
-    return {"value": px / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    what = "the unmodified reference (oracle/_ref)" if kind == "reference" else "oracle/oracle_torch.py"
+    return {"value": px / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
             "sample": f"{steps} steps of batch {CPU_B} (of 12) at 192x640, S=2, 4 scales, fwd+bwd, "
-                      f"oracle/oracle_torch.py on the host CPU, {dt:.3f} s/step"}
+                      f"{what} on the host CPU, {dt:.3f} s/step"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    step = cpu_step_fn()
+    step, kind = cpu_step_fn(B)  # the benchmark configuration itself: batch 12
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    px = CPU_B * S * NUM_SCALES * H * W
+    px = B * S * NUM_SCALES * H * W
     value = px * args.steps / dt
     cores = torch.get_num_threads()
-    sample = (f"each step = batch {CPU_B} (of 12) at 192x640, S=2, 4 scales, fwd+bwd on {cores} host threads; "
-              f"px/s is size-independent per image")
+    what = "the unmodified reference staged in oracle/_ref (compute.image2warping + compute_loss + backward)" \
+        if kind == "reference" else "the port oracle/oracle_torch.py (oracle/_ref not staged)"
+    sample = f"each step = the full batch 12 at 192x640, S=2, 4 scales, fwd+bwd on {cores} host threads, {what}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "height": H, "width": W, "sources": S,
+                   "scales": NUM_SCALES, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -472,8 +571,10 @@ def run_train_step(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    step, imgs = ts.make_step(args.loss, B, H, W, FRAME_IDS, dev, ddp=world > 1, graph=args.graph,
-                               channels_last=args.channels_last, device_pipeline=args.device_pipeline)
+    tb, th, tw, tf, layers = (8, 320, 1024, [0, -1, 1, "s"], 50) if args.config3 else (B, H, W, FRAME_IDS, 18)
+    step, imgs = ts.make_step(args.loss, tb, th, tw, tf, dev, ddp=world > 1, graph=args.graph,
+                               channels_last=args.channels_last, device_pipeline=args.device_pipeline,
+                               layers=layers, comm=args.comm, buckets=args.buckets)
     for _ in range(args.warmup):
         step()
     if world > 1:
@@ -492,13 +593,20 @@ def run_train_step(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    final_loss = float(loss.detach())
+    if hasattr(step, "close"):
+        step.close()
     if rank == 0:
         print(json.dumps({"metric": "train_images_per_sec", "value": imgs * world * args.steps / (ms * 1e-3),
                           "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                          "dtype": "f32", "data": "synthetic", "loss_impl": args.loss, "cuda_graph": bool(args.graph), "channels_last": bool(args.channels_last), "device_pipeline": bool(args.device_pipeline), "final_loss": float(loss.detach()),
-                          "config": {"workload": "mono training step: ResNet-18 depth + separate ResNet-18 pose net, "
-                                                 "batch 12 per GPU, 192x640, frame_ids [0,-1,1], 4 scales, Adam, fp32",
+                          "dtype": "f32", "data": "synthetic", "loss_impl": args.loss, "cuda_graph": bool(args.graph), "channels_last": bool(args.channels_last), "device_pipeline": bool(args.device_pipeline), "final_loss": final_loss,
+                          "comm": args.comm if (args.graph and world > 1) else ("ddp" if world > 1 else None),
+                          "config": {"workload": ("mono+stereo training step (BASELINE configs[3]): ResNet-50 depth + separate "
+                                                  "ResNet-50 pose net, batch 8 per GPU, 320x1024, frame_ids [0,-1,1,'s'], "
+                                                  "4 scales, Adam, fp32") if args.config3 else
+                                                 ("mono training step: ResNet-18 depth + separate ResNet-18 pose net, "
+                                                  "batch 12 per GPU, 192x640, frame_ids [0,-1,1], 4 scales, Adam, fp32"),
                                      "parallelism": f"ddp{world}"},
                           "clocks": clk.summary()}), flush=True)
     if world > 1:
@@ -517,6 +625,12 @@ if __name__ == "__main__":
     ap.add_argument("--device-pipeline", action="store_true",
                     help="train_step: start from uint8 frames on the device (md2_b200.pipeline) and end with md2_b200.metrics")
     ap.add_argument("--graph", action="store_true", help="train_step: replay the whole step as one CUDA graph")
+    ap.add_argument("--comm", default="captured", choices=["captured", "eager"],
+                    help="train_step --graph on N > 1 GPUs: bucket all-reduces inside the graph (overlapped with "
+                         "backward) or eagerly between a forward+backward graph and an optimizer graph")
+    ap.add_argument("--buckets", type=int, default=6, help="train_step --graph: gradient buckets")
+    ap.add_argument("--config3", action="store_true",
+                    help="train_step: BASELINE configs[3] (ResNet-50, frame_ids [0,-1,1,'s'], 320x1024, batch 8 per GPU)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.workload == "train_step":

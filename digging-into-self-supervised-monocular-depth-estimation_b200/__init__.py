@@ -17,7 +17,7 @@ __all__ = ["functional", "compute", "cabi", "build", "synthetic"]
 
 
 def __getattr__(name):
-    if name in ("functional", "compute", "build", "modules", "metrics", "pipeline"):
+    if name in ("functional", "compute", "build", "modules", "metrics", "pipeline", "selfcheck", "trainer"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -32,7 +32,8 @@ class md2_inputs(C.Structure):
                 ("K", C.c_void_p), ("inv_K", C.c_void_p),
                 ("T", C.c_void_p * MAX_SOURCES),
                 ("noise", C.c_void_p * MAX_SCALES),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64),
+                ("seed_dev", C.c_void_p)]
 
 
 class md2_outputs(C.Structure):

@@ -20,11 +20,29 @@ import torch
 from . import functional as F_
 
 
+def _base_seed():
+    """A per-object base seed for the on-device auto-mask noise: drawn from torch's global CPU generator (the one the
+    reference's torch.randn uses, processor.py:195, so torch.manual_seed makes runs repeatable) and offset by the
+    distributed rank, so that DDP ranks seeded alike still draw different noise fields."""
+    base = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+    rank = 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank = torch.distributed.get_rank()
+    return base + (rank << 32)
+
+
 class compute(object):
     def __init__(self, opt, device):
         self.opt = opt
         self.device = device
         self.step = 0
+        self.base_seed = _base_seed()
+        self._seed_t = None  # device copy of the running seed (lets a CUDA-graph replay advance it)
+        # The fused kernel indexes the pyramid by position: level i has size (H >> i, W >> i) and smoothness weight
+        # 1 / 2^i, which equals the reference's 2 ** scale (processor.py:212-214) only for scales = 0, 1, 2, ...
+        if not self._posecnn() and list(opt.scales) != list(range(len(list(opt.scales)))):
+            raise ValueError(f"md2_b200.compute: opt.scales must be [0, 1, ..., n-1] for the fused path, got "
+                             f"{list(opt.scales)} (use pose_type='posecnn' to compose the symbol-level operators)")
 
     def _posecnn(self):
         return getattr(self.opt, "pose_type", "separate") == "posecnn"
@@ -81,10 +99,25 @@ class compute(object):
         Ts = [inputs["stereo"] if f == "s" else outputs[("c2c", f, 0)] for f in srcs]
         B = inputs[("color", 0, 0)].shape[0]
         Ts = [t if t.dim() == 3 else t[None].expand(B, 4, 4) for t in Ts]
+        if self.step == 0 and not torch.cuda.is_current_stream_capturing():
+            # once per object: does torch.matmul on this build round like the kernels' table? (warns, never raises)
+            from . import selfcheck
+            selfcheck.warn_if_not_replicated(B, opt.height, opt.width, inputs[("color", 0, 0)].device)
+        seed_t = None
+        if noise is None and bool(opt.use_automasking):
+            # the running seed lives on the device and is advanced by a (graph-capturable) in-place add, so that a
+            # replayed step draws fresh auto-mask noise like the reference's per-step torch.randn (processor.py:195)
+            dev = inputs[("color", 0, 0)].device
+            if self._seed_t is None or self._seed_t.device != dev:
+                self._seed_t = torch.tensor([self.base_seed & (2 ** 62 - 1)], dtype=torch.int64, device=dev)
+            else:
+                self._seed_t.add_(1)
+            seed_t = self._seed_t
         res = F_.view_synthesis_loss(
             inputs[("color", 0, 0)], [inputs[("color", f, 0)] for f in srcs],
             [outputs[("disp", s)] for s in scales], [inputs[("color", 0, s)] for s in scales],
-            inputs[("K", 0)], inputs[("inv_K", 0)], Ts, noise=noise, seed=self.step,
+            inputs[("K", 0)], inputs[("inv_K", 0)], Ts, noise=noise, seed=self.base_seed + self.step,
+            seed_tensor=seed_t,
             automask=bool(opt.use_automasking), min_depth=opt.min_depth, max_depth=opt.max_depth,
             disp_smoothness=opt.disp_smoothness, want_per_pixel=False)
         self.step += 1

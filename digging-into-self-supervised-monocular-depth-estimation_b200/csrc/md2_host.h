@@ -133,6 +133,7 @@ inline void fill_params(Params& p, const md2_cfg* c, const md2_inputs* in, const
   }
   p.K = in->K; p.invK = in->inv_K; p.seed = in->seed;
   mix_seed(in->seed, p.seed_m1, p.seed_m2);
+  p.seed_dev = (const unsigned long long*)in->seed_dev;
   if (out) { p.per_px = out->per_pixel; p.argmin = out->argmin; p.depth = out->depth; }
   const Workspace w = workspace_layout(c);
   char* ws = (char*)workspace;

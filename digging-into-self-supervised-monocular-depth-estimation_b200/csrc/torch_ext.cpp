@@ -37,7 +37,8 @@ struct Packed {
 Packed pack(const Tensor& target, const std::vector<Tensor>& sources, const std::vector<Tensor>& disps,
             const std::vector<Tensor>& color_pyr, const Tensor& K, const Tensor& inv_K,
             const std::vector<Tensor>& Ts, const std::vector<Tensor>& noise, int64_t seed, bool automask,
-            double min_depth, double max_depth, double disp_smoothness) {
+            double min_depth, double max_depth, double disp_smoothness,
+            const c10::optional<Tensor>& seed_tensor = c10::nullopt) {
   TORCH_CHECK(target.dim() == 4 && target.size(1) == 3, "target must be [B,3,H,W], got ", target.sizes());
   const auto dev = target.device();
   const int64_t B = target.size(0), H = target.size(2), W = target.size(3);
@@ -84,6 +85,12 @@ Packed pack(const Tensor& target, const std::vector<Tensor>& sources, const std:
     }
   }
   p.in.seed = (uint64_t)seed;
+  if (seed_tensor.has_value() && seed_tensor->defined()) {
+    const Tensor& st = *seed_tensor;
+    TORCH_CHECK(st.device() == dev && st.scalar_type() == torch::kInt64 && st.numel() == 1,
+                "seed_tensor must be a one-element int64 tensor on the same device");
+    p.in.seed_dev = (const uint64_t*)st.data_ptr<int64_t>();
+  }
   return p;
 }
 
@@ -103,9 +110,10 @@ std::vector<Tensor> loss_forward(const Tensor& target, const std::vector<Tensor>
                                  const std::vector<Tensor>& disps, const std::vector<Tensor>& color_pyr,
                                  const Tensor& K, const Tensor& inv_K, const std::vector<Tensor>& Ts,
                                  const std::vector<Tensor>& noise, int64_t seed, bool automask, double min_depth,
-                                 double max_depth, double disp_smoothness, bool want_per_pixel) {
+                                 double max_depth, double disp_smoothness, bool want_per_pixel,
+                                 const c10::optional<Tensor>& seed_tensor) {
   Packed p = pack(target, sources, disps, color_pyr, K, inv_K, Ts, noise, seed, automask, min_depth, max_depth,
-                  disp_smoothness);
+                  disp_smoothness, seed_tensor);
   const c10::cuda::CUDAGuard guard(target.device());
   const auto f32 = target.options();
   const int64_t ns = p.cfg.num_scales, B = p.cfg.B, H = p.cfg.H, W = p.cfg.W;
@@ -127,9 +135,10 @@ std::vector<Tensor> loss_forward_backward(const Tensor& target, const std::vecto
                                           const Tensor& K, const Tensor& inv_K, const std::vector<Tensor>& Ts,
                                           const std::vector<Tensor>& noise, int64_t seed, bool automask,
                                           double min_depth, double max_depth, double disp_smoothness,
-                                          bool want_per_pixel, double grad_loss) {
+                                          bool want_per_pixel, double grad_loss,
+                                          const c10::optional<Tensor>& seed_tensor) {
   Packed p = pack(target, sources, disps, color_pyr, K, inv_K, Ts, noise, seed, automask, min_depth, max_depth,
-                  disp_smoothness);
+                  disp_smoothness, seed_tensor);
   const c10::cuda::CUDAGuard guard(target.device());
   const auto f32 = target.options();
   const int64_t ns = p.cfg.num_scales, B = p.cfg.B, H = p.cfg.H, W = p.cfg.W, S = p.cfg.S;

@@ -30,10 +30,10 @@ class _FusedLoss(torch.autograd.Function):
                   meta["noise"], meta["seed"], meta["automask"], meta["min_depth"], meta["max_depth"],
                   meta["disp_smoothness"], meta["want_per_pixel"])
         if need_grad:
-            r = ext().loss_forward_backward(*common, 1.0)
+            r = ext().loss_forward_backward(*common, 1.0, meta["seed_tensor"])
             ctx.grads = r[4:]
         else:
-            r = ext().loss_forward(*common)
+            r = ext().loss_forward(*common, meta["seed_tensor"])
             ctx.grads = None
         loss, per_px, argmin, depth = r[0], r[1], r[2], r[3]
         ctx.mark_non_differentiable(argmin, depth)
@@ -55,19 +55,22 @@ def view_synthesis_loss(target: torch.Tensor, sources: Sequence[torch.Tensor], d
                         color_pyr: Sequence[torch.Tensor], K: torch.Tensor, inv_K: torch.Tensor,
                         Ts: Sequence[torch.Tensor], *, noise: Optional[Sequence[torch.Tensor]] = None,
                         seed: int = 0, automask: bool = True, min_depth: float = 0.1, max_depth: float = 100.0,
-                        disp_smoothness: float = 1e-3, want_per_pixel: bool = False):
+                        disp_smoothness: float = 1e-3, want_per_pixel: bool = False,
+                        seed_tensor: Optional[torch.Tensor] = None):
     """Fused multi-scale view-synthesis loss.
 
     target [B,3,H,W]; sources S x [B,3,H,W]; disps / color_pyr per scale [B,1,h,w] / [B,3,h,w];
     K, inv_K [B,4,4]; Ts S x [B,4,4].  noise: per-scale [B,S,H,W] N(0,1) draws for the auto-mask
-    tie-breaker (processor.py:195); None draws them on the device from ``seed``.
+    tie-breaker (processor.py:195); None draws them on the device from ``seed`` - or, when ``seed_tensor`` (one int64
+    on the device) is given, from the value it holds when the kernel runs: a step captured in a CUDA graph advances
+    that tensor itself (``seed_tensor.add_(1)``), since a replay cannot change the ``seed`` argument.
     Returns dict(loss 0-dim, depth [ns,B,1,H,W], argmin [ns,B,H,W] uint8, per_pixel or None)."""
     c = lambda t: t.contiguous()
     meta = dict(ns=len(disps), S=len(sources), target=c(target), sources=[c(s) for s in sources],
                 color_pyr=[c(x) for x in color_pyr], K=c(K), inv_K=c(inv_K),
                 noise=[c(n) for n in noise] if noise is not None else [], seed=int(seed),
                 automask=bool(automask), min_depth=float(min_depth), max_depth=float(max_depth),
-                disp_smoothness=float(disp_smoothness), want_per_pixel=bool(want_per_pixel))
+                disp_smoothness=float(disp_smoothness), want_per_pixel=bool(want_per_pixel), seed_tensor=seed_tensor)
     if not torch.is_grad_enabled():
         disps = [d.detach() for d in disps]
         Ts = [t.detach() for t in Ts]

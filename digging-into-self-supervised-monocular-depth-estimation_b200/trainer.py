@@ -1,0 +1,237 @@
+"""Caller-side glue of the training step: ``trainer.batch_process`` + ``zero_grad`` + ``backward`` +
+``optimizer.step`` of /root/reference/model_train.py:54-96 replayed as ONE CUDA graph, with the gradient all-reduce of
+data-parallel training overlapped with the backward pass inside that graph.
+
+    step = GraphedTrainStep(models, batch_process, optimizer, example_inputs)      # models: setting.model (a dict)
+    for inputs in loader:
+        loss = step(inputs)                                                        # replay; loss is a device scalar
+
+``batch_process(inputs) -> outputs`` is the reference's own method (model_train.py:90-96: forward_depth, forward_pose,
+image2warping, compute_loss) or any callable built from its objects; the modules, the dict protocol and the optimizer
+are the caller's.  What this class adds:
+
+* **Flat gradient buffer.**  Every parameter's ``.grad`` is a view (same strides as the parameter, so channels-last
+  weights keep autograd's layout contract) of one contiguous fp32 buffer, cut into ``buckets`` contiguous segments in
+  reverse registration order - roughly the order in which backward produces them.
+* **Overlapped all-reduce.**  A post-accumulate hook on every parameter counts its bucket down; the hook that completes a
+  bucket enqueues ``all_reduce(bucket, AVG)`` asynchronously (NCCL over NVLink / NVSwitch on its own stream).  Under
+  capture these collectives become parallel branches of the step's graph, so they overlap the remaining backward
+  kernels exactly like DistributedDataParallel's reducer - without its per-step Python, bucket rebuilding or unused-
+  parameter search, none of which a static step needs.  ``comm="eager"`` keeps the collectives out of the graphs (one
+  graph for forward + backward, eager bucket all-reduces, one graph for the optimizer) for stacks whose NCCL cannot be
+  captured.
+* **Buffers.**  Floating-point module buffers (BatchNorm running statistics) are re-broadcast from rank 0 at the start of
+  every step, as DistributedDataParallel(broadcast_buffers=True) does.
+* **One graph.**  Static input tensors are refilled by ``copy_`` before each replay; the loss tensor is static.  The
+  auto-mask noise of md2_b200.compute stays fresh across replays because its seed lives in a device tensor the captured
+  step advances itself (functional.view_synthesis_loss(seed_tensor=...)).
+
+``graph=False`` runs the same hooks and buckets eagerly (any device, any backend): that is what the CPU / gloo tests
+exercise, and a drop-in for DistributedDataParallel when graphs are not wanted.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterable, List, Optional, Union
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+def _modules_of(models) -> List[nn.Module]:
+    if isinstance(models, nn.Module):
+        return [models]
+    if isinstance(models, dict):
+        return list(models.values())
+    return list(models)
+
+
+class FlatGradients:
+    """Parameters' gradients as views of one flat buffer, bucketed, with hook-driven asynchronous all-reduce."""
+
+    def __init__(self, params: Iterable[nn.Parameter], buckets: int = 6, process_group=None):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, device=dev, dtype=dt)
+        # reverse registration order: the last layers' gradients arrive first and fill bucket 0
+        order = list(reversed(self.params))
+        n_b = max(1, min(int(buckets), len(order)))
+        target = (total + n_b - 1) // n_b
+        self.bucket_of: Dict[int, int] = {}
+        self.bucket_range: List[List[int]] = []
+        off, b, b_start, b_count = 0, 0, 0, 0
+        self.bucket_params: List[int] = []
+        for p in order:
+            n = p.numel()
+            # same strides as the parameter (dense, possibly permuted): autograd accumulates into it in place
+            p.grad = self.flat[off:off + n].as_strided(p.size(), p.stride())
+            self.bucket_of[id(p)] = b
+            b_count += 1
+            off += n
+            if off - b_start >= target and b < n_b - 1:
+                self.bucket_range.append([b_start, off])
+                self.bucket_params.append(b_count)
+                b, b_start, b_count = b + 1, off, 0
+        self.bucket_range.append([b_start, off])
+        self.bucket_params.append(b_count)
+        self._pending = list(self.bucket_params)
+        self._works = []
+        self.hook_comm = True    # bucket all-reduces are issued from the hooks (False: reduce_now() does them)
+        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+
+    # ---- per-step protocol: begin() ... backward ... finish()
+    def begin(self):
+        self.flat.zero_()
+        self._pending = list(self.bucket_params)
+        self._works = []
+
+    def _hook(self, p):
+        b = self.bucket_of[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self.world > 1 and self.hook_comm:
+            lo, hi = self.bucket_range[b]
+            self._works.append(dist.all_reduce(self.flat[lo:hi],
+                                               op=dist.ReduceOp.AVG if self.flat.is_cuda else dist.ReduceOp.SUM,
+                                               group=self.group, async_op=True))
+
+    def finish(self):
+        """Join the outstanding collectives (and average on backends without ReduceOp.AVG)."""
+        for w in self._works:
+            w.wait()
+        self._works = []
+        if self.world > 1 and not self.flat.is_cuda and self.hook_comm:
+            self.flat.div_(self.world)
+        if any(n != 0 for n in self._pending):
+            raise RuntimeError("FlatGradients: some parameters received no gradient in this step (buckets "
+                               f"{[i for i, n in enumerate(self._pending) if n]} incomplete); the step is not static")
+
+    def reduce_now(self):
+        """All-reduce every bucket here and now (comm='eager': between the two graphs)."""
+        if self.world > 1:
+            for lo, hi in self.bucket_range:
+                dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG if self.flat.is_cuda else dist.ReduceOp.SUM,
+                                group=self.group)
+            if not self.flat.is_cuda:
+                self.flat.div_(self.world)
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+
+
+class GraphedTrainStep:
+    """One training step of the reference's trainer as a replayable CUDA graph (see the module docstring)."""
+
+    def __init__(self, models: Union[nn.Module, Dict[str, nn.Module], Iterable[nn.Module]],
+                 batch_process: Callable[[dict], dict], optimizer: torch.optim.Optimizer, example_inputs: dict, *,
+                 graph: bool = True, comm: str = "captured", buckets: int = 6, broadcast_buffers: bool = True,
+                 process_group=None, warmup: int = 3, loss_key: str = "loss"):
+        if comm not in ("captured", "eager"):
+            raise ValueError("comm must be 'captured' or 'eager'")
+        self.modules = _modules_of(models)
+        self.batch_process, self.optimizer, self.loss_key = batch_process, optimizer, loss_key
+        self.group = process_group
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.graph, self.comm = bool(graph), comm
+        params, seen = [], set()
+        for m in self.modules:
+            for p in m.parameters():
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    params.append(p)
+        if self.distributed:  # identical initial weights on every rank (what DistributedDataParallel's ctor does)
+            for p in params:
+                dist.broadcast(p.data, 0, group=process_group)
+        self.grads = FlatGradients(params, buckets, process_group)
+        self.grads.hook_comm = not (self.graph and comm == "eager")
+        self._buffers = []
+        if broadcast_buffers and self.distributed:
+            for m in self.modules:
+                self._buffers += [b for b in m.buffers() if b.is_floating_point()]
+        if self.graph:
+            if not self.grads.flat.is_cuda:
+                raise RuntimeError("GraphedTrainStep(graph=True) needs CUDA modules")
+            for g in optimizer.param_groups:  # Adam & co. keep their step counter on the device when capturable
+                if "capturable" in g:
+                    g["capturable"] = True
+        self.static_inputs = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_inputs.items()}
+        self._loss = None
+        self._graphs = None
+        if self.graph:
+            self._capture(max(int(warmup), 1))
+
+    # ---- the step body (captured, or run eagerly when graph=False)
+    def _sync_buffers(self):
+        for b in self._buffers:
+            dist.broadcast(b, 0, group=self.group)
+
+    def _forward_backward(self, inputs):
+        self._sync_buffers()
+        self.grads.begin()
+        outputs = self.batch_process(inputs)
+        loss = outputs[self.loss_key]
+        loss.backward()
+        return loss
+
+    def _body(self, inputs):
+        loss = self._forward_backward(inputs)
+        self.grads.finish()
+        if not self.grads.hook_comm:
+            self.grads.reduce_now()
+        self.optimizer.step()
+        return loss.detach()
+
+    def _capture(self, warmup):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # also creates the optimizer state, cuDNN plans and the NCCL communicator
+                self._body(self.static_inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if self.comm == "captured" or not self.distributed:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._loss = self._body(self.static_inputs)
+            self._graphs = (g,)
+        else:
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._loss = self._forward_backward(self.static_inputs).detach()
+                self.grads.finish()
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self.optimizer.step()
+            self._graphs = (g1, g2)
+
+    def __call__(self, inputs: dict):
+        if not self.graph:
+            return self._body(inputs)
+        for k, v in inputs.items():
+            if torch.is_tensor(v):
+                self.static_inputs[k].copy_(v, non_blocking=True)
+        if len(self._graphs) == 1:
+            self._graphs[0].replay()
+        else:
+            self._graphs[0].replay()
+            self.grads.reduce_now()
+            self._graphs[1].replay()
+        return self._loss
+
+    @property
+    def flat_gradients(self) -> torch.Tensor:
+        return self.grads.flat
+
+    def close(self):
+        """Release the captured graphs (they hold NCCL work when comm='captured': destroy_process_group() waits for
+        them) and the gradient hooks.  Call before tearing the process group down."""
+        if self._graphs is not None:
+            torch.cuda.synchronize()
+            for g in self._graphs:
+                g.reset()
+            self._graphs = None
+        self.grads.remove()

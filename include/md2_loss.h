@@ -63,6 +63,9 @@ typedef struct md2_inputs {
   const float* noise[MD2_MAX_SCALES];    /* N(0,1) draws of processor.py:195, [B,S,H,W] per scale;
                                             NULL => generated on the device from `seed`          */
   uint64_t seed;
+  const uint64_t* seed_dev;              /* optional DEVICE pointer: when non-NULL the seed is read from it by the
+                                            kernel instead of `seed` (a CUDA graph replays frozen parameters, so a
+                                            captured training step advances this word itself)               */
 } md2_inputs;
 
 /* Outputs of the forward part. */

@@ -1,0 +1,107 @@
+"""md2_b200.trainer.GraphedTrainStep on the B200: N replays of the captured step == N eager steps of the same modules
+(/root/reference/model_train.py:54-96).  The second test wraps the REFERENCE's own objects - its
+ResNet encoder / depth decoder / pose networks and its compute.forward_depth / forward_pose (staged in oracle/_ref) -
+with this package's compute.image2warping / compute_loss, i.e. exactly the drop-in INTEGRATION.md describes."""
+import os
+import sys
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def _run(make, n_steps, graph):
+    torch.manual_seed(0)
+    models, batch_process, params, batches = make()
+    # plain SGD with momentum: the update is linear in the gradient, so run-to-run differences stay at the level of
+    # the kernels' floating-point atomics (Adam would turn the sign of a noise-level gradient into a full lr step)
+    opt = torch.optim.SGD(params, 1e-3, momentum=0.9)
+    from md2_b200.trainer import GraphedTrainStep
+    warm = 3
+    step = GraphedTrainStep(models, batch_process, opt, batches[0], graph=graph, warmup=warm)
+    losses = []
+    if not graph:
+        for _ in range(warm):  # the graphed run spends its warm-up steps on the example batch
+            step(batches[0])
+    for i in range(n_steps):
+        losses.append(float(step(batches[i % len(batches)])))
+    torch.cuda.synchronize()
+    flat = torch.cat([p.detach().flatten() for p in params]).clone()
+    return losses, flat
+
+
+def _tiny_factory():
+    import train_step as ts
+    from md2_b200 import functional as F_
+    from md2_b200.compute import compute
+    B, H, W, fids = 2, 64, 96, [0, -1, 1]
+    nets = ts.MonoNets().to(DEV)
+    cfg = SimpleNamespace(frame_ids=fids, scales=range(4), height=H, width=W, min_depth=0.1, max_depth=100.0,
+                          pose_type="separate", use_automasking=True, disp_smoothness=1e-3)
+    comp = compute(cfg, DEV)
+    comp.base_seed = 1234  # same auto-mask noise sequence in both runs
+
+    def batch_process(inputs):
+        outputs = nets(inputs, fids)
+        for f in fids[1:]:
+            outputs[("c2c", f, 0)] = F_.param2matrix(outputs[("axisangle", f)], outputs[("translation", f)], invert=(f < 0))
+        comp.image2warping(inputs, outputs, None)
+        return comp.compute_loss(inputs, outputs, None)
+    batches = [ts.synthetic_batch(B, H, W, fids, s, torch.device(DEV)) for s in range(2)]
+    return nets, batch_process, list(nets.parameters()), batches
+
+
+def test_graph_replays_equal_eager_steps():
+    le, pe = _run(_tiny_factory, 4, graph=False)
+    lg, pg = _run(_tiny_factory, 4, graph=True)
+    for a, b in zip(le, lg):
+        assert a == pytest.approx(b, rel=2e-4), (le, lg)
+    assert float((pe - pg).abs().max()) <= 2e-5
+
+
+def _reference_factory():
+    from oracle import ref_loader as RL
+    import train_step as ts
+    from md2_b200.compute import compute as FusedCompute
+    R = RL.load()
+    sys.path.insert(0, RL.REF)
+    from model_layer import DepthDecoder, PoseDecoder, ResnetEncoder
+    B, H, W, fids = 2, 64, 96, [0, -1, 1]
+    opt = SimpleNamespace(frame_ids=fids, scales=range(4), height=H, width=W, min_depth=0.1, max_depth=100.0,
+                          pose_type="separate", pose_frames=2, use_automasking=True, disp_smoothness=1e-3, batch=B,
+                          num_layers=18, weight_init=False)
+    model = {"encoder": ResnetEncoder(18, False)}
+    model["decoder"] = DepthDecoder(model["encoder"].num_ch_enc, opt.scales)
+    model["pose_encoder"] = ResnetEncoder(18, False, 2)
+    model["pose_decoder"] = PoseDecoder(model["pose_encoder"].num_ch_enc, num_input_features=1, num_frames_to_predict_for=2)
+    model = {k: m.to(DEV).train() for k, m in model.items()}
+    setting = SimpleNamespace(model=model)
+    ref_compute = R.compute(opt, DEV)          # the reference's forward_depth / forward_pose ...
+    fused = FusedCompute(opt, DEV)             # ... and this package's image2warping / compute_loss
+    fused.base_seed = 99
+
+    def batch_process(inputs):                 # model_train.py:90-96 with the two loss calls swapped
+        outputs = {}
+        inputs, outputs = ref_compute.forward_depth(inputs, outputs, setting)
+        inputs, outputs = ref_compute.forward_pose(inputs, outputs, setting)
+        inputs, outputs = fused.image2warping(inputs, outputs, setting)
+        return fused.compute_loss(inputs, outputs, setting)
+    batches = [ts.synthetic_batch(B, H, W, fids, s, torch.device(DEV)) for s in range(2)]
+    params = [p for m in model.values() for p in m.parameters()]
+    return model, batch_process, params, batches
+
+
+def test_graphed_step_over_the_reference_trainer_objects():
+    from oracle import ref_loader as RL
+    if not RL.available():
+        pytest.skip("oracle/_ref not staged (python oracle/stage_ref.py where /root/reference exists)")
+    le, pe = _run(_reference_factory, 3, graph=False)
+    lg, pg = _run(_reference_factory, 3, graph=True)
+    for a, b in zip(le, lg):
+        assert a == pytest.approx(b, rel=2e-4), (le, lg)
+    assert float((pe - pg).abs().max()) <= 2e-5

@@ -62,7 +62,7 @@ def test_workspace_and_validation_without_gpu(lib):
 def test_struct_layout_matches_header():
     # 6 ints + 4 doubles; pointer arrays of MD2_MAX_SOURCES / MD2_MAX_SCALES
     assert C.sizeof(cabi.md2_cfg) == 6 * 4 + 4 * 8
-    assert C.sizeof(cabi.md2_inputs) == 8 * (1 + 4 + 4 + 4 + 2 + 4 + 4 + 1)
+    assert C.sizeof(cabi.md2_inputs) == 8 * (1 + 4 + 4 + 4 + 2 + 4 + 4 + 1 + 1)  # ... seed, seed_dev
     assert C.sizeof(cabi.md2_outputs) == 32
     assert C.sizeof(cabi.md2_grads) == 64
 

@@ -27,14 +27,14 @@ class Conv3x3(nn.Module):
 
 
 class Encoder(nn.Module):
-    def __init__(self, n_images=1):
+    def __init__(self, n_images=1, layers=18):
         super().__init__()
-        net = torchvision.models.resnet18(weights=None)
+        net = {18: torchvision.models.resnet18, 50: torchvision.models.resnet50}[layers](weights=None)
         net.fc = nn.Identity()  # unused head: no parameters without gradients under DDP
         if n_images > 1:
             net.conv1 = nn.Conv2d(3 * n_images, 64, 7, 2, 3, bias=False)
         self.net = net
-        self.ch = [64, 64, 128, 256, 512]
+        self.ch = [64, 64, 128, 256, 512] if layers == 18 else [64, 256, 512, 1024, 2048]
 
     def forward(self, x):
         n = self.net
@@ -94,16 +94,18 @@ class PoseDecoder(nn.Module):
 class MonoNets(nn.Module):
     """The four networks behind one module so that a single DDP wrapper covers them."""
 
-    def __init__(self):
+    def __init__(self, layers=18):
         super().__init__()
-        self.enc = Encoder(1)
+        self.enc = Encoder(1, layers)
         self.dec = DepthDecoder(self.enc.ch)
-        self.pose_enc = Encoder(2)
-        self.pose_dec = PoseDecoder(512)
+        self.pose_enc = Encoder(2, layers)
+        self.pose_dec = PoseDecoder(self.pose_enc.ch[-1])
 
     def forward(self, inputs, frame_ids):
         outputs = self.dec(self.enc(inputs[("color_aug", 0, 0)]))
         for f in frame_ids[1:]:
+            if f == "s":   # the stereo baseline is data (inputs["stereo"]), no pose network
+                continue
             pair = [inputs[("color_aug", f, 0)], inputs[("color_aug", 0, 0)]] if f < 0 else \
                    [inputs[("color_aug", 0, 0)], inputs[("color_aug", f, 0)]]
             aa, tr = self.pose_dec(self.pose_enc(torch.cat(pair, 1))[-1])
@@ -120,7 +122,8 @@ def synthetic_batch(B, H, W, frame_ids, seed, device):
     return inputs
 
 
-def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_last=False, device_pipeline=False):
+def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_last=False, device_pipeline=False,
+              layers=18, comm="captured", buckets=6):
     """Returns (step_fn, images_per_step).  loss_impl: 'fused' (md2_b200) or 'eager' (PyTorch ops).
     graph: capture forward + loss + backward + Adam in one CUDA graph (SURVEY.md 8f N3) and replay it per step;
     the batch is copied into static input buffers on the device before every replay.
@@ -128,13 +131,12 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_
     colour pyramid with md2_b200.pipeline and ends with md2_b200.metrics on a sparse 375x1242
     ground truth (N2), i.e. the whole md2_b200 surface around the stock networks."""
     from types import SimpleNamespace
-    nets = MonoNets().to(device)
+    nets = MonoNets(layers).to(device)
     if channels_last:   # NHWC activations for the cuDNN convolutions (precision-neutral); the loss inputs stay NCHW
         nets = nets.to(memory_format=torch.channels_last)
-    # With --graph the DDP wrapper is not used: capturing a DDP step never completed on this stack (torch 2.11 / NCCL
-    # 2.28.9, tried in round 1).  Instead the gradients live in one flat buffer, graph 1 replays forward + loss +
-    # backward, NCCL averages the flat buffer eagerly (one 111 MB all-reduce over NVLink), graph 2 replays Adam.
-    manual_ddp = ddp and graph
+    # With --graph the DDP wrapper is not used: md2_b200.trainer.GraphedTrainStep keeps the gradients in one flat,
+    # bucketed buffer and overlaps the bucket all-reduces with the backward pass inside the captured step (comm =
+    # "captured"), or runs them eagerly between a forward+backward graph and an optimizer graph (comm = "eager").
     model = nn.parallel.DistributedDataParallel(nets, device_ids=[device.index]) if (ddp and not graph) else nets
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graph)
     batches = [synthetic_batch(B, H, W, frame_ids, s, device) for s in range(2)]
@@ -151,19 +153,19 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_
 
         def loss_fn(inputs, outputs):
             for f in frame_ids[1:]:
-                outputs[("c2c", f, 0)] = F_.param2matrix(outputs[("axisangle", f)],
-                                                         outputs[("translation", f)], invert=(f < 0))
-            # under capture the seed would be frozen into the graph: draw the auto-mask noise with torch's
-            # graph-safe generator instead (what the reference does, processor.py:195)
-            noise = [torch.randn(B, len(frame_ids) - 1, H, W, device=device) for _ in range(4)] if graph else None
-            comp.image2warping(inputs, outputs, None, noise=noise)
+                if f != "s":
+                    outputs[("c2c", f, 0)] = F_.param2matrix(outputs[("axisangle", f)],
+                                                             outputs[("translation", f)], invert=(f < 0))
+            # the auto-mask seed lives in a device tensor the step advances itself, so a replayed graph draws fresh noise
+            comp.image2warping(inputs, outputs, None)
             return comp.compute_loss(inputs, outputs, None)["loss"]
     else:
         from oracle import oracle_torch as O  # eager PyTorch restatement of the reference loss (baseline leg)
 
         def loss_fn(inputs, outputs):
-            Ts = [O.pose_matrix(outputs[("axisangle", f)], outputs[("translation", f)],
-                                invert=(f < 0)) for f in frame_ids[1:]]
+            Ts = [inputs["stereo"] if f == "s" else
+                  O.pose_matrix(outputs[("axisangle", f)], outputs[("translation", f)], invert=(f < 0))
+                  for f in frame_ids[1:]]
             return O.view_synthesis_loss(inputs[("color", 0, 0)], [inputs[("color", f, 0)] for f in frame_ids[1:]],
                                          [outputs[("disp", s)] for s in range(4)],
                                          [inputs[("color", 0, s)] for s in range(4)], inputs[("K", 0)],
@@ -221,86 +223,17 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_
     if not graph:
         return step, B
 
-    static = {k: v.clone() for k, v in batches[0].items()}
+    from md2_b200.trainer import GraphedTrainStep
 
-    if manual_ddp:
-        import torch.distributed as dist
-        params = [p for p in model.parameters()]
-        for p in params:   # identical initial weights on every rank (what the DDP constructor would do)
-            dist.broadcast(p.data, 0)
-        for b in model.buffers():
-            dist.broadcast(b.data, 0)
-        flat = torch.zeros(sum(p.numel() for p in params), device=device)
-        off = 0
-        for p in params:
-            # same strides as the parameter (channels-last conv weights): autograd's gradient layout contract
-            p.grad = flat[off:off + p.numel()].as_strided(p.size(), p.stride())
-            off += p.numel()
+    def batch_process(inputs):
+        return {"loss": loss_fn(inputs, model(inputs, frame_ids))}
 
-        def fwd_bwd():
-            flat.zero_()
-            outputs = model(static, frame_ids)
-            loss = loss_fn(static, outputs)
-            loss.backward()          # accumulates into the views of `flat`
-            return loss
-
-        def full():
-            loss = fwd_bwd()
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            opt.step()
-            return loss
-
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                full()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
-            static_loss = fwd_bwd()
-        with torch.cuda.graph(g2, pool=g1.pool()):
-            opt.step()
-
-        def graphed_ddp_step():
-            batch = batches[state["i"] % len(batches)]
-            state["i"] += 1
-            for k, v in batch.items():
-                static[k].copy_(v)
-            g1.replay()
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            g2.replay()
-            return static_loss
-
-        return graphed_ddp_step, B
-
-    def body():
-        outputs = model(static, frame_ids)
-        loss = loss_fn(static, outputs)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return loss
-
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            body()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    opt.zero_grad(set_to_none=True)
-    with torch.cuda.graph(g):
-        static_loss = body()
+    gstep = GraphedTrainStep(nets, batch_process, opt, batches[0], graph=True, comm=comm, buckets=buckets)
 
     def graphed_step():
         batch = batches[state["i"] % len(batches)]
         state["i"] += 1
-        for k, v in batch.items():
-            static[k].copy_(v)
-        g.replay()
-        return static_loss
+        return gstep(batch)
 
+    graphed_step.close = gstep.close   # release the graphs before the process group is torn down
     return graphed_step, B
