@@ -420,11 +420,23 @@ def run_ours(args):
     barrier()
     e2e_ms_total = x0.elapsed_time(x1)
 
+    # ---- the copies alone: is the end-to-end number bound by the host link or by this code? ----------------
+    # every rank uploads its pinned batch `steps` times with nothing else running (all ranks at once, like the e2e leg)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        c0.record(copy_stream)
+        for i in range(args.steps):
+            dev_bufs[i & 1].copy_(pinned[i % n_sets][0], non_blocking=True)
+        c1.record(copy_stream)
+    barrier()
+    h2d_ms_total = c0.elapsed_time(c1)
+
     # ---- max over ranks -------------------------------------------------------------------------
-    t = torch.tensor([ms_total, e2e_ms_total, kernel_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, e2e_ms_total, kernel_ms, h2d_ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms_total, kernel_ms = [float(x) for x in t.tolist()]
+    ms_total, e2e_ms_total, kernel_ms, h2d_ms_total = [float(x) for x in t.tolist()]
     px_step = B * S * NUM_SCALES * H * W * world
     value = px_step * args.steps / (ms_total * 1e-3)
     e2e_value = px_step * args.steps / (e2e_ms_total * 1e-3)
@@ -452,6 +464,10 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms_total / args.steps,
+                "h2d_only_ms_per_step": h2d_ms_total / args.steps,
+                "h2d_only_gbps_per_rank": h2d_bytes * args.steps / (h2d_ms_total * 1e-3) / 1e9,
+                "h2d_note": "the same pinned uploads with no kernels running, all ranks at once: when this is close to "
+                            "ms_per_step the end-to-end number is bound by the host link, not by the loss",
                 "api": "md2_b200.compute.compute.image2warping + compute_loss + loss.backward(); inputs from pinned "
                        "host memory on a copy stream (step i+1 uploads while step i computes), loss read back"},
         "gpu_launches": 5 * args.steps,
@@ -474,11 +490,54 @@ def run_ours(args):
         line["speedup_vs_gpu_reference"] = {
             "as_shipped_host_randn": gpu_ref["ms_as_shipped"] / (ms_total / args.steps),
             "noise_on_device": gpu_ref["ms_noise_on_device"] / (ms_total / args.steps)}
+    # ---- the second half of BASELINE.json's metric: training images/s at this N ------------------------------
+    if not args.no_train_step:
+        try:
+            line["train_step"] = train_step_leg(dev, world, local)
+        except Exception as e:  # the headline line must survive a failure of the auxiliary leg
+            line["train_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         line["cpu_baseline"] = cpu_baseline(steps=3)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_leg(dev, world, local, steps=12, warmup=4):
+    """BASELINE.json configs[2] at this N: full mono training step (ResNet-18 depth + separate pose network on stock
+    PyTorch / cuDNN, channels-last, fused loss, Adam), batch 12 per GPU, replayed as one CUDA graph by
+    md2_b200.trainer.GraphedTrainStep with the bucket all-reduces captured inside it.  Every rank returns the dict."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import train_step as ts
+    torch.manual_seed(0)
+    step, imgs = ts.make_step("fused", B, H, W, FRAME_IDS, dev, ddp=world > 1, graph=True, channels_last=True,
+                               comm="captured", buckets=6)
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    final = float(loss.detach())
+    step.close()
+    return {"metric": "train_images_per_sec", "value": imgs * world / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
+            "steps": steps, "warmup": warmup, "n_gpus": world, "final_loss": final,
+            "mode": "fused loss, channels-last networks, whole step one CUDA graph, 6 gradient buckets all-reduced "
+                    "inside the graph (md2_b200.trainer.GraphedTrainStep)",
+            "config": "ResNet-18 depth + separate ResNet-18 pose net, batch 12 per GPU, 192x640, frame_ids [0,-1,1], "
+                      "4 scales, Adam, fp32, synthetic data, random-init weights"}
 
 
 # ------------------------------------------------------------------------------------ CPU reference
@@ -629,6 +688,8 @@ if __name__ == "__main__":
                     help="train_step --graph on N > 1 GPUs: bucket all-reduces inside the graph (overlapped with "
                          "backward) or eagerly between a forward+backward graph and an optimizer graph")
     ap.add_argument("--buckets", type=int, default=6, help="train_step --graph: gradient buckets")
+    ap.add_argument("--no-train-step", action="store_true",
+                    help="loss workload: skip the training-step leg (the `train_step` key of the JSON line)")
     ap.add_argument("--config3", action="store_true",
                     help="train_step: BASELINE configs[3] (ResNet-50, frame_ids [0,-1,1,'s'], 320x1024, batch 8 per GPU)")
     a = ap.parse_args()

@@ -149,10 +149,26 @@ class GraphedTrainStep:
                 dist.broadcast(p.data, 0, group=process_group)
         self.grads = FlatGradients(params, buckets, process_group)
         self.grads.hook_comm = not (self.graph and comm == "eager")
-        self._buffers = []
+        # floating-point buffers (BatchNorm running statistics) become views of one flat tensor, so that the per-step
+        # re-broadcast from rank 0 (DistributedDataParallel's broadcast_buffers) is ONE collective instead of ~120
+        self._buffer_flat = None
         if broadcast_buffers and self.distributed:
+            slots, seen_b = [], set()
             for m in self.modules:
-                self._buffers += [b for b in m.buffers() if b.is_floating_point()]
+                for sub in m.modules():
+                    for name, b in sub._buffers.items():
+                        if b is not None and b.is_floating_point() and id(b) not in seen_b:
+                            seen_b.add(id(b))
+                            slots.append((sub, name, b))
+            if slots:
+                flat = torch.empty(sum(b.numel() for _, _, b in slots), device=slots[0][2].device, dtype=slots[0][2].dtype)
+                off = 0
+                for sub, name, b in slots:
+                    view = flat[off:off + b.numel()].view(b.shape)
+                    view.copy_(b)
+                    sub._buffers[name] = view
+                    off += b.numel()
+                self._buffer_flat = flat
         if self.graph:
             if not self.grads.flat.is_cuda:
                 raise RuntimeError("GraphedTrainStep(graph=True) needs CUDA modules")
@@ -167,8 +183,8 @@ class GraphedTrainStep:
 
     # ---- the step body (captured, or run eagerly when graph=False)
     def _sync_buffers(self):
-        for b in self._buffers:
-            dist.broadcast(b, 0, group=self.group)
+        if self._buffer_flat is not None:
+            dist.broadcast(self._buffer_flat, 0, group=self.group)
 
     def _forward_backward(self, inputs):
         self._sync_buffers()
