@@ -97,6 +97,16 @@ MD2_FN f2 fmul2(f2 a, f2 b) { return mk2(a.x * b.x, a.y * b.y); }
 MD2_FN f2 ffma2(f2 a, f2 b, f2 c) { return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 #endif
 MD2_FN f2 bc2(float a) { return mk2(a, a); }
+
+// four consecutive floats with one 128-bit load (p is 16-byte aligned)
+#if MD2_DEVICE_BUILD
+typedef float4 f4;
+#else
+struct f4 {
+  float x, y, z, w;
+};
+#endif
+MD2_FN f4 ld4(const float* p) { return *reinterpret_cast<const f4*>(p); }
 MD2_FN f2 fsub2(f2 a, f2 b) { return ffma2(b, bc2(-1.0f), a); }  // a - b, exact product, one rounding
 
 MD2_HD int imin(int a, int b) { return a < b ? a : b; }
