@@ -17,7 +17,8 @@
 
 #include "md2_host.h"
 
-// phase-skipping experiments only (tools/variants.py): bit 0 phase A, 1 phase B, 2 phase C, 3 phase D
+// phase-skipping experiments only (tools/variants.py): bit 0 phase A, 1 phase B, 2 phase C, 3 phase D1 (row pass /
+// scale-0 reductions), 4 phase D2 (column pass), 5 the dL/dP warp reduction inside D1
 #ifndef MD2_SKIP
 #define MD2_SKIP 0
 #endif
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(TK::NT) __maxnreg__(tile_max_regs<TK>())
   TK::prologue_windows(c, tid);
   __syncthreads();
   for (int s = 0; s < p.ns; ++s) {
-    if (TK::BWD && s > 0 && !(MD2_SKIP & 8)) TK::phase_d2(c, s - 1, tid);  // column pass of the previous scale's upsample adjoint
+    if (TK::BWD && s > 0 && !(MD2_SKIP & 16)) TK::phase_d2(c, s - 1, tid);  // column pass of the previous scale's upsample adjoint
     if (!(MD2_SKIP & 1)) TK::template phase_a<DBG>(c, s, tid);
     __syncthreads();
     if (!(MD2_SKIP & 2)) TK::phase_b(c, s, tid, regs);
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(TK::NT) __maxnreg__(tile_max_regs<TK>())
       __syncthreads();
     }
   }
-  if (TK::BWD && !(MD2_SKIP & 8)) TK::phase_d2(c, p.ns - 1, tid);
+  if (TK::BWD && !(MD2_SKIP & 16)) TK::phase_d2(c, p.ns - 1, tid);
   TK::epilogue1(c, tid, regs);
   __syncthreads();
   TK::epilogue2(c, tid);
