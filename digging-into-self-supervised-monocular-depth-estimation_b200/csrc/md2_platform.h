@@ -14,10 +14,12 @@
 #define MD2_DEVICE_BUILD 1
 #define MD2_FN __device__ __forceinline__
 #define MD2_HD __host__ __device__ __forceinline__
+#define MD2_NOINLINE __device__ __noinline__
 #else
 #define MD2_DEVICE_BUILD 0
 #define MD2_FN inline
 #define MD2_HD inline
+#define MD2_NOINLINE
 #endif
 
 namespace md2 {
