@@ -82,6 +82,11 @@ class FlatGradients:
         self._pending = list(self.bucket_params)
         self._works = []
         self.hook_comm = True    # bucket all-reduces are issued from the hooks (False: reduce_now() does them)
+        # The first step calibrates: parameters that never receive a gradient (an unused classifier head of a
+        # torchvision encoder, a decoder branch of a scale that is not trained) are dropped from the bucket
+        # counts - statically, once; the step is static, so DistributedDataParallel's per-step search is not needed.
+        self._calibrating = True
+        self._fired = set()
         self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
 
     # ---- per-step protocol: begin() ... backward ... finish()
@@ -91,6 +96,9 @@ class FlatGradients:
         self._works = []
 
     def _hook(self, p):
+        if self._calibrating:
+            self._fired.add(id(p))
+            return
         b = self.bucket_of[id(p)]
         self._pending[b] -= 1
         if self._pending[b] == 0 and self.world > 1 and self.hook_comm:
@@ -101,6 +109,15 @@ class FlatGradients:
 
     def finish(self):
         """Join the outstanding collectives (and average on backends without ReduceOp.AVG)."""
+        if self._calibrating:
+            # end of the calibration step: fix the bucket counts, then reduce this step's gradients in one go
+            self._calibrating = False
+            self.unused = [p for p in self.params if id(p) not in self._fired]
+            for p in self.unused:
+                self.bucket_params[self.bucket_of[id(p)]] -= 1
+            if self.hook_comm:
+                self.reduce_now()
+            return
         for w in self._works:
             w.wait()
         self._works = []

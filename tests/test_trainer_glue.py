@@ -56,15 +56,25 @@ def test_flat_gradients_single_process_matches_plain_autograd():
         assert x.grad.data_ptr() >= step.flat_gradients.data_ptr()  # still a view of the flat buffer
 
 
-def test_incomplete_step_is_reported():
+def test_unused_parameters_are_found_once_and_a_changing_step_is_reported():
     from md2_b200.trainer import GraphedTrainStep
     a = make_nets(1)
-    extra = nn.Linear(3, 3)  # never used by batch_process: its gradients never arrive
+    extra = nn.Linear(3, 3)  # never used by batch_process (like the fc head of a torchvision encoder)
     models = dict(a, unused=extra)
     opt = torch.optim.SGD([p for m in models.values() for p in m.parameters()], 1e-2)
-    step = GraphedTrainStep(models, batch_process_of(a), opt, data(0), graph=False, buckets=2)
+    flag = {"skip_decoder": False}
+
+    def bp(inputs):
+        f = a["encoder"](inputs["color"])
+        d = f[:, :1] if flag["skip_decoder"] else a["decoder"](f)
+        return {"loss": ((d - inputs["target"]) ** 2).mean()}
+    step = GraphedTrainStep(models, bp, opt, data(0), graph=False, buckets=2)
+    step(data(0))                       # calibration step: the unused head is dropped from the bucket counts
+    assert {id(p) for p in step.grads.unused} == {id(p) for p in extra.parameters()}
+    step(data(1))                       # static step: fine
+    flag["skip_decoder"] = True         # the step changes shape: parameters that used to get gradients no longer do
     with pytest.raises(RuntimeError, match="no gradient"):
-        step(data(0))
+        step(data(2))
 
 
 def _worker(rank, world, port, ret):
