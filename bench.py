@@ -353,10 +353,12 @@ def run_ours(args):
     def consumed(k):
         return (k[0] == "color" and (k[2] == 0 or k[1] == 0)) or k[0] in ("K", "inv_K")
     # one pinned staging buffer per batch: a single H2D copy per step, the dict entries are views of it
-    pinned = []
+    # What a training step receives from the HOST is the loader's batch (images, intrinsics); the disparities and the
+    # poses are network outputs and already live on the device (model_train.py:90-96), so they are not uploaded.
+    pinned, dev_outputs = [], []
     for inputs, outputs in host:
-        items = [(("in", k), v) for k, v in inputs.items() if consumed(k)] + \
-                [(("out", k), v) for k, v in outputs.items() if k[0] in ("disp", "c2c")]
+        items = [(("in", k), v) for k, v in inputs.items() if consumed(k)]
+        dev_outputs.append({k: v.to(dev) for k, v in outputs.items() if k[0] in ("disp", "c2c")})
         total = sum((v.numel() + 63) // 64 * 64 for _, v in items)
         flat = torch.empty(total, dtype=torch.float32).pin_memory()
         layout, off = [], 0
@@ -394,13 +396,8 @@ def run_ours(args):
             upload(i + 1)
         with torch.cuda.stream(main_stream):
             main_stream.wait_event(ev)
-            inputs, outputs = {}, {}
-            for (kind, key), off, n, shape in layout:
-                v = dflat[off:off + n].view(shape)
-                if kind == "in":
-                    inputs[key] = v
-                else:
-                    outputs[key] = v.requires_grad_(True)
+            inputs = {key: dflat[off:off + n].view(shape) for (kind, key), off, n, shape in layout}
+            outputs = {k: v.detach().requires_grad_(True) for k, v in dev_outputs[i % n_sets].items()}
             comp.image2warping(inputs, outputs, None)
             comp.compute_loss(inputs, outputs, None)
             outputs["loss"].backward()
@@ -468,8 +465,10 @@ def run_ours(args):
                 "h2d_only_gbps_per_rank": h2d_bytes * args.steps / (h2d_ms_total * 1e-3) / 1e9,
                 "h2d_note": "the same pinned uploads with no kernels running, all ranks at once: when this is close to "
                             "ms_per_step the end-to-end number is bound by the host link, not by the loss",
-                "api": "md2_b200.compute.compute.image2warping + compute_loss + loss.backward(); inputs from pinned "
-                       "host memory on a copy stream (step i+1 uploads while step i computes), loss read back"},
+                "api": "md2_b200.compute.compute.image2warping + compute_loss + loss.backward(); the loader's batch "
+                       "(target pyramid, source frames, K, inv_K) from pinned host memory on a copy stream (step i+1 "
+                       "uploads while step i computes), disparities / poses on the device like network outputs, loss "
+                       "read back"},
         "gpu_launches": 5 * args.steps,
         "split_calls_ms": {"md2_loss_forward": fwd_ms, "md2_loss_backward": bwd_ms,
                            "md2_loss_forward_backward": ms_total / args.steps},
