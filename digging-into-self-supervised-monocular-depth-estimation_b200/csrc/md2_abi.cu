@@ -122,6 +122,20 @@ __global__ void __launch_bounds__(TK::NT) __maxnreg__(tile_max_regs<TK>())
   TK::make_ctx(c, p, sm, blockIdx.x, blockIdx.y, blockIdx.z);
   typename TK::Regs regs;
   TK::init_regs(regs);
+  if (TK::BWD && MD2_STAGGER_MODE != 0) {
+    // Phase staggering.  All CTAs do the same work in the same time, so the two CTAs that share an SM would run in
+    // lockstep - both in the fp32-bound phase B, then both in the latency-bound phases A and C - and the pipes one
+    // phase leaves idle would stay idle.  Delaying the second CTA of every SM in the FIRST wave by about half a
+    // scale iteration puts them out of phase for the whole launch (their successors inherit the offset).
+    const unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    unsigned nsm;
+    asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    const bool second = MD2_STAGGER_MODE == 1 ? (lin >= nsm && lin < 2 * nsm) : (lin < 2 * nsm && (lin & 1));
+    if (second) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)MD2_STAGGER_CYCLES) __nanosleep(256);
+    }
+  }
   if (p.use_tma) {
     // TMA: one thread issues the box loads, everybody computes K.T meanwhile, then waits on the mbarrier
     tma_stage_tiles<TK>(c, p, maps, sm, tid);
@@ -314,6 +328,13 @@ struct TileEvents {
 constexpr int kMaxDevices = 64;
 
 // occupancy experiments only (tools/variants.py): extra dynamic shared memory per CTA
+// phase staggering of the co-resident CTAs (see tile_kernel): 0 off, 1 the CTAs nsm..2*nsm-1, 2 the odd CTAs below 2*nsm
+#ifndef MD2_STAGGER_MODE
+#define MD2_STAGGER_MODE 0
+#endif
+#ifndef MD2_STAGGER_CYCLES
+#define MD2_STAGGER_CYCLES 16000
+#endif
 #ifndef MD2_EXTRA_SMEM
 #define MD2_EXTRA_SMEM 0
 #endif
