@@ -20,8 +20,10 @@ are the caller's.  What this class adds:
   parameter search, none of which a static step needs.  ``comm="eager"`` keeps the collectives out of the graphs (one
   graph for forward + backward, eager bucket all-reduces, one graph for the optimizer) for stacks whose NCCL cannot be
   captured.
-* **Buffers.**  Floating-point module buffers (BatchNorm running statistics) are re-broadcast from rank 0 at the start of
-  every step, as DistributedDataParallel(broadcast_buffers=True) does.
+* **Buffers.**  Floating-point module buffers (BatchNorm running statistics) are views of one flat tensor that is
+  re-broadcast from rank 0 once per step (DistributedDataParallel(broadcast_buffers=True) does it with one broadcast
+  per buffer at the start of the forward pass; here it is one collective, issued after the forward pass and
+  overlapped with backward).
 * **One graph.**  Static input tensors are refilled by ``copy_`` before each replay; the loss tensor is static.  The
   auto-mask noise of md2_b200.compute stays fresh across replays because its seed lives in a device tensor the captured
   step advances itself (functional.view_synthesis_loss(seed_tensor=...)).
@@ -109,6 +111,9 @@ class FlatGradients:
 
     def finish(self):
         """Join the outstanding collectives (and average on backends without ReduceOp.AVG)."""
+        for w in self._works:
+            w.wait()
+        self._works = []
         if self._calibrating:
             # end of the calibration step: fix the bucket counts, then reduce this step's gradients in one go
             self._calibrating = False
@@ -118,9 +123,6 @@ class FlatGradients:
             if self.hook_comm:
                 self.reduce_now()
             return
-        for w in self._works:
-            w.wait()
-        self._works = []
         if self.world > 1 and not self.flat.is_cuda and self.hook_comm:
             self.flat.div_(self.world)
         if any(n != 0 for n in self._pending):
@@ -199,15 +201,15 @@ class GraphedTrainStep:
             self._capture(max(int(warmup), 1))
 
     # ---- the step body (captured, or run eagerly when graph=False)
-    def _sync_buffers(self):
-        if self._buffer_flat is not None:
-            dist.broadcast(self._buffer_flat, 0, group=self.group)
-
     def _forward_backward(self, inputs):
-        self._sync_buffers()
         self.grads.begin()
         outputs = self.batch_process(inputs)
         loss = outputs[self.loss_key]
+        # The running statistics are final once the forward pass is done (training-mode BatchNorm normalises with the
+        # batch statistics and only UPDATES the buffers), so their re-broadcast from rank 0 travels beside the
+        # backward pass instead of in front of the next forward pass, where DistributedDataParallel puts it.
+        if self._buffer_flat is not None:
+            self.grads._works.append(dist.broadcast(self._buffer_flat, 0, group=self.group, async_op=True))
         loss.backward()
         return loss
 
