@@ -6,8 +6,8 @@
 //   1. smooth_forward_kernel   per (scale, image, row band): sums for the mean-normalised
 //                              smoothness (model_loss.py:77-88,112-116);
 //  1b. smooth_backward_kernel  (backward) gradient of the smoothness term;
-//   2. tile_kernel<S, BWD>     one CTA per 32x16 image tile, all scales and sources
-//                              (md2_tile.cuh);
+//   2. tile_kernel<S, BWD>     one CTA per 32 x TH image tile, all scales and sources
+//                              (md2_tile.cuh; 3 CTA barriers per scale);
 //   3. finalize_kernel         fixed-order reduction of the per-CTA partials -> loss,
 //                              dL/dT = K^T dL/dP.
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime (no -lcuda)
