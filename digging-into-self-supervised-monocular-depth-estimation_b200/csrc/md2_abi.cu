@@ -17,6 +17,14 @@
 
 #include "md2_host.h"
 
+// phase staggering of the co-resident CTAs (see tile_kernel): 0 off, 1 the CTAs nsm..2*nsm-1, 2 the odd CTAs below 2*nsm
+#ifndef MD2_STAGGER_MODE
+#define MD2_STAGGER_MODE 0
+#endif
+#ifndef MD2_STAGGER_CYCLES
+#define MD2_STAGGER_CYCLES 16000
+#endif
+
 // phase-skipping experiments only (tools/variants.py): bit 0 phase A, 1 phase B, 2 phase C, 3 phase D1 (row pass /
 // scale-0 reductions), 4 phase D2 (column pass), 5 the dL/dP warp reduction inside D1
 #ifndef MD2_SKIP
@@ -123,10 +131,10 @@ __global__ void __launch_bounds__(TK::NT) __maxnreg__(tile_max_regs<TK>())
   typename TK::Regs regs;
   TK::init_regs(regs);
   if (TK::BWD && MD2_STAGGER_MODE != 0) {
-    // Phase staggering.  All CTAs do the same work in the same time, so the two CTAs that share an SM would run in
-    // lockstep - both in the fp32-bound phase B, then both in the latency-bound phases A and C - and the pipes one
-    // phase leaves idle would stay idle.  Delaying the second CTA of every SM in the FIRST wave by about half a
-    // scale iteration puts them out of phase for the whole launch (their successors inherit the offset).
+    // Phase-staggering experiment (off by default; measured: no effect, profiles/r2_experiments.json).  If the two
+    // CTAs that share an SM ran in lockstep - both in the fp32-bound phase B, then both in the latency-bound phases A
+    // and C - delaying the second CTA of every SM in the FIRST wave by about half a scale iteration would put them
+    // out of phase for the whole launch (their successors inherit the offset).
     const unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     unsigned nsm;
     asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
@@ -328,13 +336,6 @@ struct TileEvents {
 constexpr int kMaxDevices = 64;
 
 // occupancy experiments only (tools/variants.py): extra dynamic shared memory per CTA
-// phase staggering of the co-resident CTAs (see tile_kernel): 0 off, 1 the CTAs nsm..2*nsm-1, 2 the odd CTAs below 2*nsm
-#ifndef MD2_STAGGER_MODE
-#define MD2_STAGGER_MODE 0
-#endif
-#ifndef MD2_STAGGER_CYCLES
-#define MD2_STAGGER_CYCLES 16000
-#endif
 #ifndef MD2_EXTRA_SMEM
 #define MD2_EXTRA_SMEM 0
 #endif
