@@ -81,6 +81,11 @@ def _reference_factory():
     model["pose_decoder"] = PoseDecoder(model["pose_encoder"].num_ch_enc, num_input_features=1, num_frames_to_predict_for=2)
     model = {k: m.to(DEV).train() for k, m in model.items()}
     setting = SimpleNamespace(model=model)
+    # The reference's param2matrix builds its matrices on the host and copies them over (model_layer/warp.py:50,111),
+    # which a CUDA graph cannot capture: the symbol-level drop-in replaces it.
+    import model_tool.processor as ref_processor
+    from md2_b200 import functional as F_
+    ref_processor.param2matrix = F_.param2matrix
     ref_compute = R.compute(opt, DEV)          # the reference's forward_depth / forward_pose ...
     fused = FusedCompute(opt, DEV)             # ... and this package's image2warping / compute_loss
     fused.base_seed = 99
