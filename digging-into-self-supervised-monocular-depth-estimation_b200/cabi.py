@@ -74,7 +74,7 @@ OPS_PROTOTYPES = {
 }
 EXPORTS += list(OPS_PROTOTYPES) + ["md2_metrics_workspace_bytes", "md2_depth_metrics", "md2_pyramid_tables_bytes",
                                    "md2_pyramid_tables_fill", "md2_pyramid_workspace_bytes", "md2_color_pyramid",
-                                   "md2_jitter_workspace_bytes", "md2_color_jitter"]
+                                   "md2_jitter_workspace_bytes", "md2_color_jitter", "md2_to_tensor"]
 
 
 class md2_jitter_cfg(C.Structure):
@@ -86,6 +86,14 @@ class md2_jitter_cfg(C.Structure):
 class md2_pyramid_cfg(C.Structure):
     """include/md2_pipeline.h"""
     _fields_ = [("N", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("H", C.c_int), ("W", C.c_int), ("scales", C.c_int)]
+
+
+class md2_u8_images(C.Structure):
+    """include/md2_pipeline.h"""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int)]
+
+
+MD2_TO_TENSOR_MAX = 16
 
 
 class md2_metrics_cfg(C.Structure):
@@ -159,6 +167,8 @@ def load_library(path=None):
     lib.md2_color_pyramid.restype = C.c_int
     lib.md2_color_pyramid.argtypes = [C.POINTER(md2_pyramid_cfg), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
+    lib.md2_to_tensor.restype = C.c_int
+    lib.md2_to_tensor.argtypes = [C.c_int, C.POINTER(md2_u8_images), C.c_void_p]
     for name, argtypes in OPS_PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -332,6 +332,51 @@ static void launch_h(int rows, int pitch, const LevelTab& t, const unsigned* pla
 }
 
 
+// ---- ToTensor on the device --------------------------------------------------------------------------------------
+// transforms.ToTensor() of kitti_mono.py:283 (called at :352, :364): uint8 HWC -> float32 CHW, .div(255).  The loader
+// keeps the resized PIL images as bytes and the step uploads those (a quarter of the float bytes); one launch converts
+// every image group of the batch.  Four pixels per thread where the row length allows it: three aligned 32-bit loads
+// (12 bytes = 4 RGB pixels), one 16-byte store per channel plane.
+struct ToTensorJobs {
+  const uint8_t* src[MD2_TO_TENSOR_MAX];
+  float* dst[MD2_TO_TENSOR_MAX];
+  int hw[MD2_TO_TENSOR_MAX];          // pixels per image
+  int n[MD2_TO_TENSOR_MAX];           // images
+  unsigned first_block[MD2_TO_TENSOR_MAX + 1];
+  int count;
+};
+
+__global__ void __launch_bounds__(256) to_tensor_kernel(const __grid_constant__ ToTensorJobs jobs) {
+  int j = 0;
+  while (j + 1 < jobs.count && blockIdx.x >= jobs.first_block[j + 1]) ++j;
+  const int hw = jobs.hw[j];
+  const size_t total = (size_t)jobs.n[j] * hw;  // pixels of the group
+  const uint8_t* __restrict__ src = jobs.src[j];
+  float* __restrict__ dst = jobs.dst[j];
+  const size_t q = ((size_t)(blockIdx.x - jobs.first_block[j]) * 256 + threadIdx.x) * 4;  // first pixel of this thread
+  if (q >= total) return;
+  const size_t img = q / hw;
+  const int p = (int)(q - img * hw);
+  float* o = dst + img * 3 * (size_t)hw + p;
+  if ((hw & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(src + q * 3);
+    const uint32_t a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2);  // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+    *reinterpret_cast<float4*>(o) =
+        make_float4(div255(a & 255), div255(a >> 24), div255((b >> 16) & 255), div255((c >> 8) & 255));
+    *reinterpret_cast<float4*>(o + hw) =
+        make_float4(div255((a >> 8) & 255), div255(b & 255), div255(b >> 24), div255((c >> 16) & 255));
+    *reinterpret_cast<float4*>(o + 2 * (size_t)hw) =
+        make_float4(div255((a >> 16) & 255), div255((b >> 8) & 255), div255(c & 255), div255(c >> 24));
+  } else {
+    for (int k = 0; k < 4 && q + k < total; ++k) {
+      const size_t qq = q + k;
+      const size_t im = qq / hw;
+      const int pp = (int)(qq - im * hw);
+      for (int ch = 0; ch < 3; ++ch) dst[(im * 3 + ch) * (size_t)hw + pp] = div255(src[qq * 3 + ch]);
+    }
+  }
+}
+
 }  // namespace md2
 
 using namespace md2;
@@ -400,6 +445,35 @@ int md2_color_pyramid(const md2_pyramid_cfg* cfg, const uint8_t* images, const u
   }
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
+}
+
+int md2_to_tensor(int count, const md2_u8_images* groups, md2_stream_t stream) {
+  if (count == 0) return 0;
+  if (!groups) return MD2_ERR_NULL;
+  if (count < 0 || count > MD2_TO_TENSOR_MAX) return MD2_ERR_SHAPE;
+  md2::ToTensorJobs jobs;
+  unsigned blocks = 0;
+  int used = 0;
+  for (int i = 0; i < count; ++i) {
+    const md2_u8_images& g = groups[i];
+    if (g.N < 0 || g.H < 0 || g.W < 0) return MD2_ERR_SHAPE;
+    const long long px = (long long)g.N * g.H * g.W;
+    if (px == 0) continue;  // an empty group converts nothing
+    if (!g.src || !g.dst) return MD2_ERR_NULL;
+    if ((long long)g.H * g.W > 0x7fffffffLL || px > (1LL << 40)) return MD2_ERR_SHAPE;
+    jobs.src[used] = g.src;
+    jobs.dst[used] = g.dst;
+    jobs.hw[used] = g.H * g.W;
+    jobs.n[used] = g.N;
+    jobs.first_block[used] = blocks;
+    blocks += (unsigned)((px + 1023) / 1024);
+    ++used;
+  }
+  if (used == 0) return 0;
+  jobs.first_block[used] = blocks;
+  jobs.count = used;
+  md2::to_tensor_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(jobs);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

@@ -77,6 +77,47 @@ class ColorPyramid:
         return outs
 
 
+def to_tensor(images, out=None):
+    """transforms.ToTensor() on the device (kitti_mono.py:283, applied at :352 / :364): uint8 CUDA tensors
+    [N,H,W,3] (the loader's resized PIL images as bytes) -> float32 [N,3,H,W] = v / 255, bit-identical to
+    torchvision's.  ``images`` is one tensor or a list (the levels of the target pyramid, the source frames, ...):
+    the whole list is converted by ONE launch (chunks of 16 groups).  A training step that uploads bytes and calls
+    this moves a quarter of the host-link traffic of uploading the loader's float tensors.  ``out``: optional
+    preallocated float32 tensors of the matching shapes."""
+    single = isinstance(images, torch.Tensor)
+    imgs = [images] if single else list(images)
+    if not imgs:
+        return []
+    dev = imgs[0].device
+    for t in imgs:
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.dim() == 4 and t.shape[3] == 3
+                and t.device == dev):
+            raise RuntimeError("to_tensor: expected uint8 CUDA tensors [N,H,W,3] on one device; md2_b200 has no CPU path "
+                               f"(got {getattr(t, 'dtype', type(t))} {tuple(getattr(t, 'shape', ()))})")
+    imgs = [t.contiguous() for t in imgs]
+    if out is None:
+        outs = [torch.empty(t.shape[0], 3, t.shape[1], t.shape[2], dtype=torch.float32, device=dev) for t in imgs]
+    else:
+        outs = [out] if isinstance(out, torch.Tensor) else list(out)
+        if len(outs) != len(imgs):
+            raise RuntimeError("to_tensor: one output per input")
+        for t, o in zip(imgs, outs):
+            if not (o.is_cuda and o.device == dev and o.dtype == torch.float32 and o.is_contiguous()
+                    and tuple(o.shape) == (t.shape[0], 3, t.shape[1], t.shape[2])):
+                raise RuntimeError("to_tensor: out must be contiguous float32 [N,3,H,W] on the inputs' device")
+    lib = _L()
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for k in range(0, len(imgs), cabi.MD2_TO_TENSOR_MAX):
+            chunk = list(zip(imgs, outs))[k:k + cabi.MD2_TO_TENSOR_MAX]
+            groups = (cabi.md2_u8_images * len(chunk))(*[
+                cabi.md2_u8_images(t.data_ptr(), o.data_ptr(), t.shape[0], t.shape[1], t.shape[2]) for t, o in chunk])
+            rc = lib.md2_to_tensor(len(chunk), groups, stream)
+            if rc != 0:
+                raise RuntimeError(f"md2_to_tensor failed with code {rc}")
+    return outs[0] if single else outs
+
+
 class ColorJitter:
     """The jitter of KITTIMonoDataset_v2 (kitti_mono.py:281-282): ``ColorJitter.get_params((0.8, 1.2), (0.8, 1.2),
     (0.8, 1.2), (-0.1, 0.1))`` draws the four factors and a shuffled order once, like torchvision <= 0.8 did, and

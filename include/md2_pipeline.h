@@ -60,6 +60,20 @@ size_t md2_jitter_workspace_bytes(const md2_jitter_cfg* cfg);
 int md2_color_jitter(const md2_jitter_cfg* cfg, const float* in, const uint8_t* apply, float* out, void* workspace,
                      md2_stream_t stream);
 
+/* transforms.ToTensor() on the device (model_loader/kitti_mono.py:283, applied at :352 and :364; kitti_stereo.py:50,
+ * :130-153): uint8 [N,H,W,3] (the resized PIL image as bytes) -> float32 [N,3,H,W] = v / 255 correctly rounded, i.e.
+ * bit-identical to torchvision's to_tensor (third-party; `img.permute(2,0,1).to(float32).div(255)`).  The loader keeps
+ * bytes, the training step uploads a quarter of the float traffic and converts here.  One launch for up to
+ * MD2_TO_TENSOR_MAX image groups (the target pyramid's levels, the source frames, ...); `groups` is a HOST array.
+ * Groups with N*H*W == 0 are skipped. */
+#define MD2_TO_TENSOR_MAX 16
+typedef struct md2_u8_images {
+  const uint8_t* src; /* device, [N,H,W,3] uint8  */
+  float* dst;         /* device, [N,3,H,W] float32 */
+  int N, H, W;
+} md2_u8_images;
+int md2_to_tensor(int count, const md2_u8_images* groups, md2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

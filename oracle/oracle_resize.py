@@ -69,6 +69,14 @@ def resize_antialias(img, H, W):
     return out
 
 
+def to_tensor(img):
+    """transforms.ToTensor() of kitti_mono.py:283 (applied at :352, :364) on uint8 images: [..., H, W, 3] uint8 ->
+    [..., 3, H, W] float32, v / 255 (torchvision's to_tensor: permute, .to(float32), .div(255) - an IEEE division)."""
+    a = np.asarray(img)
+    assert a.dtype == np.uint8 and a.shape[-1] == 3
+    return np.ascontiguousarray(np.moveaxis(a, -1, -3)).astype(np.float32) / np.float32(255)
+
+
 def color_pyramid(img, H, W, scales=4, flip=False):
     """kitti_mono.py:296-304 (flip), :283-288 + :352-355 (resize every level from the original), ToTensor:
     uint8 [Hin,Win,3] -> list of float32 [3, H>>s, W>>s]."""

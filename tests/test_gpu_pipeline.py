@@ -76,6 +76,72 @@ def test_every_byte_value_converts_like_totensor():
     assert np.array_equal(out, ref)
 
 
+def test_to_tensor_matches_oracle_bit_exact():
+    """md2_to_tensor (kitti_mono.py:283 on the device): every byte value; row lengths that are / are not multiples
+    of four pixels; several groups in one launch, more groups than one launch takes, an empty group."""
+    import md2_b200.pipeline as P
+    from oracle import oracle_resize as R
+    rng = np.random.default_rng(11)
+    every = np.arange(256, dtype=np.uint8).repeat(3 * 4).reshape(1, 16, 64, 3)
+    shapes = [(12, 192, 640), (12, 96, 320), (12, 48, 160), (12, 24, 80), (3, 7, 9), (1, 1, 1), (2, 5, 6), (0, 4, 4),
+              (1, 33, 130)]
+    imgs = [every] + [rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8) for n, h, w in shapes]
+    dev = [torch.from_numpy(a).to(DEV) for a in imgs]
+    outs = P.to_tensor(dev)
+    assert len(outs) == len(imgs)
+    for a, o in zip(imgs, outs):
+        ref = R.to_tensor(a) if a.size else np.zeros((a.shape[0], 3, a.shape[1], a.shape[2]), np.float32)
+        assert o.dtype == torch.float32 and tuple(o.shape) == ref.shape
+        assert np.array_equal(o.cpu().numpy(), ref)
+    # a single tensor in, a single tensor out; preallocated outputs; more than MD2_TO_TENSOR_MAX groups
+    one = P.to_tensor(dev[1])
+    assert torch.equal(one, outs[1])
+    pre = torch.full_like(outs[2], -1.0)
+    assert P.to_tensor(dev[2], out=pre) is pre and torch.equal(pre, outs[2])
+    many = P.to_tensor([dev[5]] * 19 + [dev[6]])
+    assert len(many) == 20 and all(torch.equal(m, outs[5]) for m in many[:19]) and torch.equal(many[19], outs[6])
+    # an unaligned view of the bytes takes the scalar path and still matches
+    flat = torch.zeros(3 * 8 * 12 * 3 + 1, dtype=torch.uint8, device=DEV)
+    flat[1:] = torch.from_numpy(imgs[1].reshape(-1)[:3 * 8 * 12 * 3].copy()).to(DEV)
+    shifted = flat[1:].view(3, 8, 12, 3)
+    assert np.array_equal(P.to_tensor(shifted).cpu().numpy(), R.to_tensor(shifted.cpu().numpy()))
+    with pytest.raises(RuntimeError):
+        P.to_tensor(torch.from_numpy(imgs[1]))                    # host tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        P.to_tensor(dev[1].float())                               # wrong dtype
+    with pytest.raises(RuntimeError):
+        P.to_tensor(dev[1].permute(0, 3, 1, 2))                   # not HWC
+
+
+def test_loss_from_uploaded_bytes_equals_loss_from_float_tensors():
+    """The training step that uploads bytes and converts on the device computes the same loss, per-pixel maps and
+    argmin, bit for bit, as the one that receives the loader's float tensors (ToTensor on the host)."""
+    import md2_b200.cabi as cabi
+    import md2_b200.pipeline as P
+    from oracle import oracle_resize as R
+    from test_gpu_parity import synth_args
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, H, W = 2, 64, 96
+    args = synth_args(B, H, W, [0, -1, 1], True, "smooth", 21)
+    rng = np.random.default_rng(5)
+    u8 = {"pyr": [rng.integers(0, 256, (B, H >> s, W >> s, 3), dtype=np.uint8) for s in range(4)],
+          "src": [rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8) for _ in range(2)]}
+    host = dict(args)
+    host["color_pyr"] = [torch.from_numpy(R.to_tensor(a)).to(DEV) for a in u8["pyr"]]
+    host["target"] = host["color_pyr"][0]
+    host["sources"] = [torch.from_numpy(R.to_tensor(a)).to(DEV) for a in u8["src"]]
+    conv = P.to_tensor([torch.from_numpy(a).to(DEV) for a in u8["pyr"] + u8["src"]])
+    devc = dict(args)
+    devc["color_pyr"], devc["target"], devc["sources"] = conv[:4], conv[0], conv[4:]
+    cl = cabi.CLoss()
+    a, b = cl.forward_backward(host), cl.forward_backward(devc)
+    assert float(a["loss"]) == float(b["loss"])
+    assert torch.equal(a["per_pixel"], b["per_pixel"]) and torch.equal(a["argmin"], b["argmin"])
+    from helpers import norm_rel
+    for s in range(4):   # identical inputs; the gradient scatter uses float atomics, whose order is not fixed
+        assert norm_rel(a["grad_disp"][s], b["grad_disp"][s]) <= 1e-6
+
+
 def _jitter_ref(img_u8, order, b, c, s, h):
     import torchvision.transforms.functional as F
     from PIL import Image

@@ -99,3 +99,42 @@ def test_intrinsics_match_reference_golden():
     for s in range(4):
         assert np.array_equal(intr[("K", s)].numpy(), z[f"K{s}"])
         assert np.array_equal(intr[("inv_K", s)].numpy(), z[f"inv_K{s}"])
+
+
+def test_to_tensor_oracle_is_torchvisions_totensor():
+    """kitti_mono.py:283 - transforms.ToTensor() on the loader's PIL images: every byte value in every channel, and
+    the golden level-0 image the reference's own objects produced (tests/golden/pyramid.npz)."""
+    import torch
+    from PIL import Image
+    from torchvision import transforms
+    img = np.arange(256, dtype=np.uint8).repeat(3 * 5).reshape(16, 80, 3)[:, ::-1].copy()
+    img[..., 1] = img[..., 1][::-1]
+    ref = transforms.ToTensor()(Image.fromarray(img)).numpy()
+    got = R.to_tensor(img)
+    assert got.dtype == np.float32 and got.shape == (3, 16, 80) and np.array_equal(got, ref)
+    batch = np.random.default_rng(3).integers(0, 256, (2, 7, 9, 3), dtype=np.uint8)
+    ref_b = np.stack([transforms.ToTensor()(Image.fromarray(b)).numpy() for b in batch])
+    assert np.array_equal(R.to_tensor(batch), ref_b)
+    z = _golden()
+    lvl0 = R.resize_antialias(z["image"], 64, 192)
+    assert np.array_equal(R.to_tensor(lvl0), z["color_f0_s0"])
+
+
+def test_to_tensor_entry_point_validates_without_gpu():
+    """include/md2_pipeline.h md2_to_tensor: argument errors and empty work return before any launch."""
+    import md2_b200.build as b
+    import md2_b200.cabi as cabi
+    b.build_cuda_library()
+    lib = cabi.load_library()
+    one = cabi.md2_u8_images(8, 8, 1, 4, 4)
+    arr = (cabi.md2_u8_images * 1)(one)
+    assert lib.md2_to_tensor(0, None, None) == 0
+    assert lib.md2_to_tensor(1, None, None) == cabi.MD2_ERR_NULL
+    assert lib.md2_to_tensor(cabi.MD2_TO_TENSOR_MAX + 1, arr, None) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_to_tensor(-1, arr, None) == cabi.MD2_ERR_SHAPE
+    bad = (cabi.md2_u8_images * 1)(cabi.md2_u8_images(8, 8, 1, -4, 4))
+    assert lib.md2_to_tensor(1, bad, None) == cabi.MD2_ERR_SHAPE
+    null_src = (cabi.md2_u8_images * 1)(cabi.md2_u8_images(0, 8, 1, 4, 4))
+    assert lib.md2_to_tensor(1, null_src, None) == cabi.MD2_ERR_NULL
+    empty = (cabi.md2_u8_images * 2)(cabi.md2_u8_images(0, 0, 0, 4, 4), cabi.md2_u8_images(0, 0, 3, 0, 4))
+    assert lib.md2_to_tensor(2, empty, None) == 0            # nothing to convert, nothing launched
