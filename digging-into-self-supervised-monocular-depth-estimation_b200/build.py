@@ -22,7 +22,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
 def _newer(target, sources):
@@ -43,7 +43,7 @@ def _run(cmd, verbose):
 
 
 def build_cuda_library(force=False, verbose=False, ptxas_verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("md2_abi.cu", "md2_l1.cu", "md2_metrics.cu", "md2_pipeline.cu", "md2_jitter.cu", "md2_tile.cuh", "md2_platform.h",
+    srcs = [os.path.join(CSRC, f) for f in ("md2_abi.cu", "md2_l1.cu", "md2_metrics.cu", "md2_pipeline.cu", "md2_jitter.cu", "md2_tile.cuh", "md2_platform.h", "md2_nvtx.h",
                                                "md2_host.h")]
     srcs += [os.path.join(ROOT, "include", h) for h in ("md2_loss.h", "md2_ops.h", "md2_metrics.h", "md2_pipeline.h")]
     if not force and _newer(LIB, srcs):

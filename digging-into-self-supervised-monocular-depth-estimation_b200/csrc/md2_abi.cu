@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "md2_host.h"
+#include "md2_nvtx.h"
 
 // phase staggering of the co-resident CTAs (see tile_kernel): 0 off, 1 the CTAs nsm..2*nsm-1, 2 the odd CTAs below 2*nsm
 #ifndef MD2_STAGGER_MODE
@@ -490,16 +491,19 @@ size_t md2_workspace_bytes(const md2_cfg* cfg) {
 
 int md2_loss_forward(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out, void* workspace,
                      md2_stream_t stream) {
+  const NvtxRange range("md2_loss_forward");
   return run_step(cfg, in, out, nullptr, 1.0f, nullptr, nullptr, workspace, stream, kForward, nullptr);
 }
 
 int md2_loss_forward_backward(const md2_cfg* cfg, const md2_inputs* in, const md2_outputs* out,
                               const md2_grads* grads, float grad_loss, void* workspace, md2_stream_t stream) {
+  const NvtxRange range("md2_loss_forward_backward");
   return run_step(cfg, in, out, grads, grad_loss, nullptr, nullptr, workspace, stream, kFused, nullptr);
 }
 
 int md2_loss_backward(const md2_cfg* cfg, const md2_inputs* in, const uint8_t* argmin, const float* grad_loss_dev,
                       const md2_grads* grads, void* workspace, md2_stream_t stream) {
+  const NvtxRange range("md2_loss_backward");
   return run_step(cfg, in, nullptr, grads, 1.0f, grad_loss_dev, argmin, workspace, stream, kBackward, nullptr);
 }
 
@@ -560,6 +564,7 @@ int md2_loss_forward_backward_timed(const md2_cfg* cfg, const md2_inputs* in, co
                                     void* start_event, void* stop_event) {
   if (!start_event || !stop_event) return MD2_ERR_NULL;
   const TileEvents ev = {(cudaEvent_t)start_event, (cudaEvent_t)stop_event};
+  const NvtxRange range("md2_loss_forward_backward");
   return run_step(cfg, in, out, grads, grad_loss, nullptr, nullptr, workspace, stream, kFused, nullptr, &ev);
 }
 

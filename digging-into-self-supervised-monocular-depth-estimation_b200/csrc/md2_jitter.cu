@@ -6,6 +6,7 @@
 
 #include "../../include/md2_pipeline.h"
 #include "md2_host.h"
+#include "md2_nvtx.h"
 
 namespace md2 {
 
@@ -159,6 +160,7 @@ size_t md2_jitter_workspace_bytes(const md2_jitter_cfg* cfg) {
 
 int md2_color_jitter(const md2_jitter_cfg* cfg, const float* in, const uint8_t* apply, float* out, void* workspace,
                      md2_stream_t stream) {
+  const md2::NvtxRange range("md2_color_jitter");
   const int v = validate_jitter(cfg);
   if (v != 0) return v;
   if (!in || !out) return MD2_ERR_NULL;

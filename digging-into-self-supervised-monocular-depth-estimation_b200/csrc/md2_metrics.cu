@@ -14,6 +14,7 @@
 
 #include "../../include/md2_metrics.h"
 #include "md2_host.h"
+#include "md2_nvtx.h"
 
 namespace md2 {
 
@@ -237,6 +238,7 @@ size_t md2_metrics_workspace_bytes(const md2_metrics_cfg* cfg) {
 
 int md2_depth_metrics(const md2_metrics_cfg* cfg, const float* depth, const float* gt, float* out, void* workspace,
                       md2_stream_t stream) {
+  const md2::NvtxRange range("md2_depth_metrics");
   const int v = validate_metrics(cfg);
   if (v != 0) return v;
   if (!depth || !gt || !out) return MD2_ERR_NULL;

@@ -16,6 +16,7 @@
 
 #include "../../include/md2_pipeline.h"
 #include "md2_host.h"
+#include "md2_nvtx.h"
 
 namespace md2 {
 
@@ -410,6 +411,7 @@ size_t md2_pyramid_workspace_bytes(const md2_pyramid_cfg* cfg) {
 
 int md2_color_pyramid(const md2_pyramid_cfg* cfg, const uint8_t* images, const uint8_t* flip, const void* device_tables,
                       float* const* out, void* workspace, md2_stream_t stream) {
+  const md2::NvtxRange range("md2_color_pyramid");
   const int v = validate_pyramid(cfg);
   if (v != 0) return v;
   if (!images || !device_tables || !out) return MD2_ERR_NULL;
@@ -448,6 +450,7 @@ int md2_color_pyramid(const md2_pyramid_cfg* cfg, const uint8_t* images, const u
 }
 
 int md2_to_tensor(int count, const md2_u8_images* groups, md2_stream_t stream) {
+  const md2::NvtxRange range("md2_to_tensor");
   if (count == 0) return 0;
   if (!groups) return MD2_ERR_NULL;
   if (count < 0 || count > MD2_TO_TENSOR_MAX) return MD2_ERR_SHAPE;

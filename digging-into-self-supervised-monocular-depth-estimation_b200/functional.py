@@ -45,10 +45,10 @@ class _FusedLoss(torch.autograd.Function):
     def backward(ctx, g_loss, *_):
         if ctx.grads is None:
             raise RuntimeError("fused loss was run without gradients")
-        out = [None]
-        for i, g in enumerate(ctx.grads):
-            out.append(g * g_loss if ctx.needs_input_grad[1 + i] else None)
-        return tuple(out)
+        need = [i for i in range(len(ctx.grads)) if ctx.needs_input_grad[1 + i]]
+        # one multi-tensor launch instead of one multiply per gradient
+        scaled = dict(zip(need, torch._foreach_mul([ctx.grads[i] for i in need], g_loss)))
+        return (None,) + tuple(scaled.get(i) for i in range(len(ctx.grads)))
 
 
 def view_synthesis_loss(target: torch.Tensor, sources: Sequence[torch.Tensor], disps: Sequence[torch.Tensor],
