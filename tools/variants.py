@@ -16,7 +16,7 @@ for spec in sys.argv[1:]:
     flags = [f for f in flags.split(",") if f]
     lib = os.path.join(OUT, f"libmd2loss_{name}.so")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-           "-shared", "-Xptxas", "-v", *flags, *SRCS, "-o", lib]
+           "-shared", "-ldl", "-Xptxas", "-v", *flags, *SRCS, "-o", lib]
     procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
 for name, p in procs:
     out = p.communicate()[0]
