@@ -24,6 +24,10 @@ are the caller's.  What this class adds:
   re-broadcast from rank 0 once per step (DistributedDataParallel(broadcast_buffers=True) does it with one broadcast
   per buffer at the start of the forward pass; here it is one collective, issued after the forward pass and
   overlapped with backward).
+* **Learning-rate schedules survive capture.**  For optimizers with a ``capturable`` mode (Adam, AdamW, ...) the
+  learning rate of every parameter group becomes a device tensor, which ``torch.optim.lr_scheduler`` updates in place
+  (the reference steps a StepLR per epoch, model_train.py:81; model_tool/loader.py:107-108).  Other optimizers bake
+  their hyper-parameters into the graph: build a new GraphedTrainStep after changing them.
 * **One graph.**  Static input tensors are refilled by ``copy_`` before each replay; the loss tensor is static.  The
   auto-mask noise of md2_b200.compute stays fresh across replays because its seed lives in a device tensor the captured
   step advances itself (functional.view_synthesis_loss(seed_tensor=...)).
@@ -194,6 +198,11 @@ class GraphedTrainStep:
             for g in optimizer.param_groups:  # Adam & co. keep their step counter on the device when capturable
                 if "capturable" in g:
                     g["capturable"] = True
+                    # ... and read a TENSOR learning rate at replay time: torch's schedulers update such a tensor in
+                    # place (model_train.py:81 steps a StepLR every epoch), whereas a Python float would be frozen
+                    # into the captured kernels' arguments and the schedule silently ignored
+                    if not torch.is_tensor(g["lr"]):
+                        g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=self.grads.flat.device)
         self.static_inputs = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_inputs.items()}
         self._loss = None
         self._graphs = None

@@ -110,3 +110,44 @@ def test_graphed_step_over_the_reference_trainer_objects():
     for a, b in zip(le, lg):
         assert a == pytest.approx(b, rel=2e-4), (le, lg)
     assert float((pe - pg).abs().max()) <= 2e-5
+
+
+def test_lr_schedule_reaches_the_captured_optimizer():
+    """model_train.py:81 steps a StepLR between epochs (model_tool/loader.py:107-108: Adam + StepLR).  A captured Adam
+    step must follow it: same parameters as the eager loop after the learning rate has dropped three times."""
+    import copy
+    from md2_b200.trainer import GraphedTrainStep
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ELU(), torch.nn.Linear(32, 4)).to(DEV)
+    ref = copy.deepcopy(net)
+    xs = [torch.randn(64, 16, device=DEV) for _ in range(6)]
+    ys = [torch.randn(64, 4, device=DEV) for _ in range(6)]
+
+    def process(m):
+        return lambda inputs: {"loss": ((m(inputs["x"]) - inputs["y"]) ** 2).mean()}
+
+    opt = torch.optim.Adam(net.parameters(), 1e-2)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 1, gamma=0.1)
+    step = GraphedTrainStep(net, process(net), opt, {"x": xs[0], "y": ys[0]}, warmup=1)
+    # the warm-up + capture steps have moved `net`: restart both from the same point, with fresh optimizer state
+    net.load_state_dict(ref.state_dict())
+    for st in opt.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    ref_opt = torch.optim.Adam(ref.parameters(), 1e-2)
+    ref_sched = torch.optim.lr_scheduler.StepLR(ref_opt, 1, gamma=0.1)
+    for i in range(6):
+        step({"x": xs[i], "y": ys[i]})
+        ref_opt.zero_grad(set_to_none=True)
+        process(ref)({"x": xs[i], "y": ys[i]})["loss"].backward()
+        ref_opt.step()
+        if i % 2 == 1:                      # an "epoch" of two steps
+            sched.step()
+            ref_sched.step()
+    assert torch.is_tensor(opt.param_groups[0]["lr"])
+    assert float(opt.param_groups[0]["lr"]) == pytest.approx(1e-5, rel=1e-5)
+    assert float(ref_opt.param_groups[0]["lr"]) == pytest.approx(1e-5, rel=1e-5)
+    for a, b in zip(net.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), float((a - b).abs().max())
+    step.close()
