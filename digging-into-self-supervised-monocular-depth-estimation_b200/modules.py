@@ -325,3 +325,71 @@ class _MeanInvDepth(torch.autograd.Function):
 def mean_inv_depth(depth):
     """(1 / depth).mean(3, True).mean(2, True) of processor.py:155 -> [B,1,1,1]."""
     return _MeanInvDepth.apply(depth)
+
+
+# ----------------------------------------------------------------------------- ReflectionPad2d (decoder Conv3x3)
+class _ReflectionPad2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad):
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+            raise RuntimeError(f"ReflectionPad2d: expected a 4-D float32 CUDA tensor (got {getattr(x, 'dtype', type(x))} "
+                               f"{tuple(getattr(x, 'shape', ()))} on {getattr(x, 'device', '?')}); md2_b200 has no CPU path")
+        N, Cc, H, W = x.shape
+        pl, pr, pt, pb = pad
+        if min(pad) < 0 or pl >= W or pr >= W or pt >= H or pb >= H:
+            raise RuntimeError(f"ReflectionPad2d: padding {pad} must be non-negative and smaller than the input "
+                               f"dimensions {(H, W)}")
+        # NHWC stays NHWC, anything else is handled as contiguous NCHW
+        cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        x = x if cl else x.contiguous()
+        out = torch.empty((N, Cc, H + pt + pb, W + pl + pr), device=x.device, dtype=torch.float32,
+                          memory_format=torch.channels_last if cl else torch.contiguous_format)
+        if out.numel():
+            with torch.cuda.device(x.device):
+                _check(_L().md2_reflection_pad2d_forward(N, Cc, H, W, pl, pr, pt, pb, int(cl), _p(x), _p(out), _st()),
+                       "md2_reflection_pad2d_forward")
+        ctx.cfg = (N, Cc, H, W, pad, cl)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, Cc, H, W, (pl, pr, pt, pb), cl = ctx.cfg
+        fmt = torch.channels_last if cl else torch.contiguous_format
+        g = g.contiguous(memory_format=fmt)
+        gi = torch.empty((N, Cc, H, W), device=g.device, dtype=torch.float32, memory_format=fmt)
+        if gi.numel():
+            with torch.cuda.device(g.device):
+                _check(_L().md2_reflection_pad2d_backward(N, Cc, H, W, pl, pr, pt, pb, int(cl), _p(g), _p(gi), _st()),
+                       "md2_reflection_pad2d_backward")
+        return gi, None
+
+
+class ReflectionPad2d(nn.Module):
+    """nn.ReflectionPad2d for the decoder's Conv3x3 (depth_decoder.py:40, warp.py:179) that keeps the tensor's memory
+    format: a channels-last input gives a channels-last output (ATen's operator converts to NCHW and back, forward
+    and backward).  ``padding``: int or (left, right, top, bottom).  Drop-in:
+    ``conv3x3.pad = md2_b200.modules.ReflectionPad2d(1)``; values bit-identical to nn.ReflectionPad2d."""
+
+    def __init__(self, padding):
+        super().__init__()
+        self.padding = (int(padding),) * 4 if isinstance(padding, int) else tuple(int(p) for p in padding)
+        if len(self.padding) != 4:
+            raise ValueError("ReflectionPad2d: padding must be an int or (left, right, top, bottom)")
+
+    def forward(self, x):
+        return _ReflectionPad2d.apply(x, self.padding)
+
+    def extra_repr(self):
+        return f"{self.padding}"
+
+
+def use_channels_last_padding(module: nn.Module) -> int:
+    """Replace every nn.ReflectionPad2d inside ``module`` (the reference's Conv3x3 blocks) by ReflectionPad2d above;
+    returns how many were replaced.  Call it next to ``module.to(memory_format=torch.channels_last)``."""
+    n = 0
+    for parent in module.modules():
+        for name, child in list(parent.named_children()):
+            if type(child) is nn.ReflectionPad2d:
+                setattr(parent, name, ReflectionPad2d(tuple(child.padding)))
+                n += 1
+    return n

@@ -28,6 +28,9 @@ are the caller's.  What this class adds:
   learning rate of every parameter group becomes a device tensor, which ``torch.optim.lr_scheduler`` updates in place
   (the reference steps a StepLR per epoch, model_train.py:81; model_tool/loader.py:107-108).  Other optimizers bake
   their hyper-parameters into the graph: build a new GraphedTrainStep after changing them.
+* **Fused optimizer.**  An untouched ``torch.optim.Adam(params, lr)`` (model_tool/loader.py:107) runs as ~10 multi-tensor
+  kernels per step; with ``fuse_optimizer=True`` (default) a fresh optimizer whose groups leave ``fused`` / ``foreach``
+  at their defaults is switched to torch's fused implementation before capture (same update rule, one pass).
 * **One graph.**  Static input tensors are refilled by ``copy_`` before each replay; the loss tensor is static.  The
   auto-mask noise of md2_b200.compute stays fresh across replays because its seed lives in a device tensor the captured
   step advances itself (functional.view_synthesis_loss(seed_tensor=...)).
@@ -153,7 +156,7 @@ class GraphedTrainStep:
     def __init__(self, models: Union[nn.Module, Dict[str, nn.Module], Iterable[nn.Module]],
                  batch_process: Callable[[dict], dict], optimizer: torch.optim.Optimizer, example_inputs: dict, *,
                  graph: bool = True, comm: str = "captured", buckets: int = 6, broadcast_buffers: bool = True,
-                 process_group=None, warmup: int = 3, loss_key: str = "loss"):
+                 process_group=None, warmup: int = 3, loss_key: str = "loss", fuse_optimizer: bool = True):
         if comm not in ("captured", "eager"):
             raise ValueError("comm must be 'captured' or 'eager'")
         self.modules = _modules_of(models)
@@ -203,6 +206,14 @@ class GraphedTrainStep:
                     # into the captured kernels' arguments and the schedule silently ignored
                     if not torch.is_tensor(g["lr"]):
                         g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=self.grads.flat.device)
+                    # A fresh Adam-family optimizer left at torch's default (foreach: ~10 multi-tensor kernels per
+                    # step) is switched to its fused implementation - one pass over parameters and moments (measured:
+                    # 21.5 -> 20.4 ms per step of the ResNet-18 configuration).  Same update rule; an optimizer that
+                    # already has state, or whose caller chose foreach / fused explicitly, is left alone.
+                    if (fuse_optimizer and "fused" in g and g.get("fused") is None and g.get("foreach") is None
+                            and len(optimizer.state) == 0
+                            and all(p.is_cuda and torch.is_floating_point(p) for p in g["params"])):
+                        g["fused"] = True
         self.static_inputs = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_inputs.items()}
         self._loss = None
         self._graphs = None

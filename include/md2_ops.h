@@ -73,6 +73,18 @@ int md2_mean_inv_depth_forward(int B, int n, const float* depth, float* out, md2
 int md2_mean_inv_depth_backward(int B, int n, const float* depth, const float* g_out, float* g_depth,
                                 md2_stream_t stream);
 
+/* nn.ReflectionPad2d((pad_l, pad_r, pad_t, pad_b)) of the decoder's Conv3x3 blocks (model_layer/depth_decoder.py:36-50,
+ * model_layer/warp.py:175-190), in the memory format the tensor already has: channels_last != 0 means the buffers are
+ * NHWC ([N,H,W,C] in memory, torch.channels_last), 0 means contiguous NCHW.  ATen's operator only knows NCHW, which costs
+ * a channels-last network two layout copies per pad and per direction; this one keeps NHWC tensors NHWC (float4 moves
+ * when C % 4 == 0).  in [N,C,H,W] -> out [N,C,H+pad_t+pad_b,W+pad_l+pad_r], bit-identical to ATen; every pad must be
+ * smaller than its axis (MD2_ERR_SHAPE otherwise, like torch's error).  Backward: g_in is overwritten with the sum of
+ * the <= 9 padded positions that read each element, added in a fixed order (ATen accumulates with atomics). */
+int md2_reflection_pad2d_forward(int N, int C, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
+                                 int channels_last, const float* in, float* out, md2_stream_t stream);
+int md2_reflection_pad2d_backward(int N, int C, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
+                                  int channels_last, const float* g_out, float* g_in, md2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

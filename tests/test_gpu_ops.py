@@ -279,3 +279,58 @@ def test_compute_posecnn_branch(M):
     rg = torch.autograd.grad(ref["loss"], b["disps"] + [b["R"][-1], b["R"][1], b["T"][-1], b["T"][1]])
     for x, y in zip(grads, rg):
         _close(x, y, 1e-3)
+
+
+# ----------------------------------------------------------------------------- ReflectionPad2d (decoder Conv3x3)
+@pytest.mark.parametrize("shape,pad,cl", [
+    ((2, 16, 12, 20), 1, True),               # the decoder's case: channels-last, C % 4 == 0 (float4 path)
+    ((2, 16, 12, 20), 1, False),              # contiguous NCHW
+    ((3, 6, 7, 9), (2, 1, 3, 0), True),       # channels-last, C % 4 != 0 (scalar path), asymmetric pads
+    ((1, 8, 5, 4), (3, 3, 4, 4), True),       # pads of size - 1: every mirror overlaps
+    ((2, 3, 2, 2), (1, 1, 1, 1), False),      # 2 x 2 planes: an element is read up to 9 times
+    ((1, 1, 6, 6), 2, True),                  # C == 1: channels-last and NCHW coincide
+    ((12, 32, 96, 320), 1, True),             # a real decoder level
+])
+def test_reflection_pad2d_matches_aten(shape, pad, cl):
+    """model_layer/depth_decoder.py:36-50 (Conv3x3.pad): forward bit-identical to nn.ReflectionPad2d in both memory
+    formats, output in the input's format; backward equal to ATen's (integer-valued gradients make every summation
+    order exact, so the comparison is bit-exact)."""
+    import md2_b200.modules as M
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(*shape, generator=g).to(DEV)
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    x = x.contiguous(memory_format=fmt)
+    xa = x.detach().clone().requires_grad_(True)
+    xb = x.detach().clone().contiguous(memory_format=fmt).requires_grad_(True)
+    ours, ref = M.ReflectionPad2d(pad)(xb), torch.nn.ReflectionPad2d(pad)(xa)
+    assert ours.shape == ref.shape and torch.equal(ours, ref)
+    assert ours.is_contiguous(memory_format=fmt)
+    go = torch.randint(-8, 9, ref.shape, generator=g).float().to(DEV).contiguous(memory_format=fmt)
+    ours.backward(go)
+    ref.backward(go)
+    assert torch.equal(xb.grad, xa.grad)
+    assert xb.grad.is_contiguous(memory_format=fmt)
+    # real-valued gradients: equal up to the order of at most nine additions
+    gr = torch.randn(ref.shape, generator=g).to(DEV)
+    (g1,) = torch.autograd.grad(M.ReflectionPad2d(pad)(xb), xb, gr)
+    (g2,) = torch.autograd.grad(torch.nn.ReflectionPad2d(pad)(xa), xa, gr)
+    assert torch.allclose(g1, g2, rtol=1e-6, atol=1e-6)
+
+
+def test_reflection_pad2d_rejects_bad_input_and_swaps_into_modules():
+    import md2_b200.modules as M
+    x = torch.randn(1, 4, 5, 5, device=DEV)
+    with pytest.raises(RuntimeError):
+        M.ReflectionPad2d(5)(x)                       # pad must be smaller than the axis (torch raises too)
+    with pytest.raises(RuntimeError):
+        M.ReflectionPad2d(1)(x.cpu())                 # no CPU path
+    with pytest.raises(RuntimeError):
+        M.ReflectionPad2d(1)(x.double())
+    with pytest.raises(RuntimeError):
+        M.ReflectionPad2d(1)(x[0])                    # 3-D
+    net = torch.nn.Sequential(torch.nn.ReflectionPad2d(1), torch.nn.Conv2d(4, 8, 3),
+                              torch.nn.Sequential(torch.nn.ReflectionPad2d((1, 0, 2, 1)), torch.nn.ELU())).to(DEV)
+    ref = net(x)
+    assert M.use_channels_last_padding(net) == 2
+    assert isinstance(net[0], M.ReflectionPad2d) and net[2][0].padding == (1, 0, 2, 1)
+    assert torch.equal(net(x), ref)

@@ -43,6 +43,11 @@ def test_operator_entry_points_validate_without_gpu(lib):
     assert lib.md2_project_forward(1, 1, 8, one, one, one, 1e-7, one, null) == cabi.MD2_ERR_SHAPE
     assert lib.md2_project_backward(1, 8, 8, one, one, one, 1e-7, one, one, null, null) == cabi.MD2_ERR_NULL
     assert lib.md2_grid_sample_forward(1, 0, 8, 8, 8, 8, one, one, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_reflection_pad2d_forward(1, 4, 4, 4, 4, 0, 0, 0, 1, one, one, null) == cabi.MD2_ERR_SHAPE  # pad >= W
+    assert lib.md2_reflection_pad2d_forward(1, 4, 4, 4, 1, 1, 1, -1, 0, one, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_reflection_pad2d_forward(1, 4, 4, 4, 1, 1, 1, 1, 1, null, one, null) == cabi.MD2_ERR_NULL
+    assert lib.md2_reflection_pad2d_backward(0, 4, 4, 4, 1, 1, 1, 1, 1, one, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_reflection_pad2d_backward(1, 4, 4, 4, 1, 1, 1, 1, 0, one, null, null) == cabi.MD2_ERR_NULL
     assert lib.md2_reprojection_forward(1, 2, 8, one, one, one, null) == cabi.MD2_ERR_SHAPE
     assert lib.md2_smooth_forward(1, 8, 8, one, one, null, one, null) == cabi.MD2_ERR_NULL
 

@@ -10,6 +10,8 @@ nearest x2 up-sampling, sigmoid disparities at 4 scales; pose decoder on the las
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -131,14 +133,24 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_
     colour pyramid with md2_b200.pipeline and ends with md2_b200.metrics on a sparse 375x1242
     ground truth (N2), i.e. the whole md2_b200 surface around the stock networks."""
     from types import SimpleNamespace
+    # the reference switches cuDNN's autotuner on (model_utility.py:327-328); shapes are static, so it pays once
+    torch.backends.cudnn.benchmark = os.environ.get("MD2_CUDNN_BENCHMARK", "1") == "1"
     nets = MonoNets(layers).to(device)
     if channels_last:   # NHWC activations for the cuDNN convolutions (precision-neutral); the loss inputs stay NCHW
         nets = nets.to(memory_format=torch.channels_last)
+        if loss_impl == "fused" and os.environ.get("MD2_STOCK_PAD", "0") != "1":
+            # ATen's reflection pad only knows NCHW: every Conv3x3 would pay layout copies around it, forward and
+            # backward.  md2_b200.modules.ReflectionPad2d is the same operator (bit-identical) that keeps NHWC tensors NHWC.
+            from md2_b200.modules import use_channels_last_padding
+            use_channels_last_padding(nets)
     # With --graph the DDP wrapper is not used: md2_b200.trainer.GraphedTrainStep keeps the gradients in one flat,
     # bucketed buffer and overlaps the bucket all-reduces with the backward pass inside the captured step (comm =
     # "captured"), or runs them eagerly between a forward+backward graph and an optimizer graph (comm = "eager").
     model = nn.parallel.DistributedDataParallel(nets, device_ids=[device.index]) if (ddp and not graph) else nets
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graph)
+    # same Adam as model_tool/loader.py:107; the fused multi-tensor implementation makes one pass over the parameters
+    # (None = torch's default, the multi-kernel foreach implementation)
+    fused = True if (device.type == "cuda" and os.environ.get("MD2_FUSED_ADAM", "1") == "1") else None
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=graph, fused=fused)
     batches = [synthetic_batch(B, H, W, frame_ids, s, device) for s in range(2)]
     if channels_last:
         for b in batches:
