@@ -151,3 +151,41 @@ def test_lr_schedule_reaches_the_captured_optimizer():
     for a, b in zip(net.parameters(), ref.parameters()):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), float((a - b).abs().max())
     step.close()
+
+
+def test_channels_last_padding_in_the_reference_decoder():
+    """md2_b200.modules.use_channels_last_padding on the REFERENCE's DepthDecoder (model_layer/depth_decoder.py:36-50):
+    same disparities and the same parameter gradients as with nn.ReflectionPad2d, tensors stay channels-last."""
+    from oracle import ref_loader as RL
+    if not RL.available():
+        pytest.skip("oracle/_ref not staged (python oracle/stage_ref.py where /root/reference exists)")
+    import copy
+    import md2_b200.modules as M
+    RL.load()
+    sys.path.insert(0, RL.REF)
+    from model_layer import DepthDecoder, ResnetEncoder
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False     # compare the operators, not cuDNN's TF32 algorithm choice per layout
+    try:
+        torch.manual_seed(1)
+        enc = ResnetEncoder(18, False).to(DEV).to(memory_format=torch.channels_last).eval()
+        dec = DepthDecoder(enc.num_ch_enc, range(4)).to(DEV).to(memory_format=torch.channels_last)
+        dec2 = copy.deepcopy(dec)
+        n = M.use_channels_last_padding(dec2)
+        assert n == sum(isinstance(m, M.ReflectionPad2d) for m in dec2.modules()) and n >= 10
+        assert not any(type(m) is torch.nn.ReflectionPad2d for m in dec2.modules())
+        x = torch.rand(2, 3, 64, 96, device=DEV).contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            feats = enc(x)
+        outs = []
+        for d in (dec, dec2):
+            o = d([f.clone() for f in feats])
+            disp = [o[("disp", s)] for s in range(4)]
+            sum((t * t).mean() for t in disp).backward()
+            outs.append((disp, [p.grad.clone() for p in d.parameters()]))
+        for a, b in zip(outs[0][0], outs[1][0]):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+        for a, b in zip(outs[0][1], outs[1][1]):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-7), float((a - b).abs().max())
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
