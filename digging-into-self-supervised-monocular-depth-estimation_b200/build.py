@@ -43,12 +43,12 @@ def _run(cmd, verbose):
 
 
 def build_cuda_library(force=False, verbose=False, ptxas_verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("md2_abi.cu", "md2_l1.cu", "md2_metrics.cu", "md2_pipeline.cu", "md2_jitter.cu", "md2_pad.cu", "md2_tile.cuh", "md2_platform.h", "md2_nvtx.h",
+    srcs = [os.path.join(CSRC, f) for f in ("md2_abi.cu", "md2_l1.cu", "md2_metrics.cu", "md2_pipeline.cu", "md2_jitter.cu", "md2_pad.cu", "md2_pool.cu", "md2_tile.cuh", "md2_platform.h", "md2_nvtx.h",
                                                "md2_host.h")]
     srcs += [os.path.join(ROOT, "include", h) for h in ("md2_loss.h", "md2_ops.h", "md2_metrics.h", "md2_pipeline.h")]
     if not force and _newer(LIB, srcs):
         return LIB
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_verbose else []) + srcs[:6] + ["-o", LIB]
+    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_verbose else []) + srcs[:7] + ["-o", LIB]
     out = _run(cmd, verbose)
     if ptxas_verbose:
         print(out)

@@ -73,6 +73,8 @@ OPS_PROTOTYPES = {
     "md2_mean_inv_depth_backward": [_I, _I, _V, _V, _V, _V],
     "md2_reflection_pad2d_forward": [_I] * 9 + [_V, _V, _V],
     "md2_reflection_pad2d_backward": [_I] * 9 + [_V, _V, _V],
+    "md2_maxpool2d_nhwc_forward": [_I] * 7 + [_V, _V, _V, _V],
+    "md2_maxpool2d_nhwc_backward": [_I] * 7 + [_V, _V, _V, _V],
 }
 EXPORTS += list(OPS_PROTOTYPES) + ["md2_metrics_workspace_bytes", "md2_depth_metrics", "md2_pyramid_tables_bytes",
                                    "md2_pyramid_tables_fill", "md2_pyramid_workspace_bytes", "md2_color_pyramid",

@@ -383,6 +383,84 @@ class ReflectionPad2d(nn.Module):
         return f"{self.padding}"
 
 
+# ----------------------------------------------------------------------------- MaxPool2d (encoder stem)
+class _MaxPool2dNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, s, p):
+        N, Cc, H, W = x.shape
+        Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        if H + 2 * p < k or W + 2 * p < k or Ho <= 0 or Wo <= 0:
+            raise RuntimeError(f"MaxPool2d: input {(H, W)} too small for kernel {k}, padding {p}")
+        out = torch.empty((N, Cc, Ho, Wo), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        win = torch.empty((N, Cc, Ho, Wo), device=x.device, dtype=torch.uint8, memory_format=torch.channels_last)
+        with torch.cuda.device(x.device):
+            _check(_L().md2_maxpool2d_nhwc_forward(N, Cc, H, W, k, s, p, _p(x), _p(out), _p(win), _st()),
+                   "md2_maxpool2d_nhwc_forward")
+        ctx.save_for_backward(win)
+        ctx.cfg = (N, Cc, H, W, k, s, p)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (win,) = ctx.saved_tensors
+        N, Cc, H, W, k, s, p = ctx.cfg
+        g = g.contiguous(memory_format=torch.channels_last)
+        gi = torch.empty((N, Cc, H, W), device=g.device, dtype=torch.float32, memory_format=torch.channels_last)
+        with torch.cuda.device(g.device):
+            _check(_L().md2_maxpool2d_nhwc_backward(N, Cc, H, W, k, s, p, _p(g), _p(win), _p(gi), _st()),
+                   "md2_maxpool2d_nhwc_backward")
+        return gi, None, None, None
+
+
+class MaxPool2d(nn.Module):
+    """nn.MaxPool2d(kernel_size, stride, padding) of the ResNet encoders (depth_encoder.py:29) for channels-last
+    tensors: bit-identical values, one byte of state per output instead of an int64 index, and a backward that gathers
+    instead of scattering with atomics.  Square kernel / stride / padding, dilation 1, ceil_mode False.  A tensor that
+    is not channels-last (or has C == 1, where the formats coincide) is converted first: this module is meant for
+    networks run in torch.channels_last."""
+
+    def __init__(self, kernel_size, stride=None, padding=0):
+        super().__init__()
+        self.kernel_size, self.padding = int(kernel_size), int(padding)
+        self.stride = int(stride) if stride is not None else int(kernel_size)
+        if not (0 < self.kernel_size <= 15 and self.stride > 0 and 0 <= 2 * self.padding <= self.kernel_size):
+            raise ValueError("MaxPool2d: kernel_size in 1..15, stride > 0, padding <= kernel_size / 2")
+
+    def forward(self, x):
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+            raise RuntimeError(f"MaxPool2d: expected a 4-D float32 CUDA tensor (got {getattr(x, 'dtype', type(x))} "
+                               f"{tuple(getattr(x, 'shape', ()))} on {getattr(x, 'device', '?')}); md2_b200 has no CPU path")
+        return _MaxPool2dNHWC.apply(x.contiguous(memory_format=torch.channels_last), self.kernel_size, self.stride,
+                                    self.padding)
+
+    def extra_repr(self):
+        return f"kernel_size={self.kernel_size}, stride={self.stride}, padding={self.padding}"
+
+
+def _square(v):
+    if isinstance(v, int):
+        return v
+    v = tuple(v)
+    return v[0] if len(set(v)) == 1 else None
+
+
+def use_channels_last_pooling(module: nn.Module) -> int:
+    """Replace every plain nn.MaxPool2d inside ``module`` (square window, dilation 1, ceil_mode False, no indices
+    returned - the encoders' stem, depth_encoder.py:29) by MaxPool2d above; returns how many were replaced."""
+    n = 0
+    for parent in module.modules():
+        for name, child in list(parent.named_children()):
+            if type(child) is not nn.MaxPool2d or child.ceil_mode or child.return_indices:
+                continue
+            k, s, p, d = (_square(child.kernel_size), _square(child.stride if child.stride is not None else child.kernel_size),
+                          _square(child.padding), _square(child.dilation))
+            if None in (k, s, p) or d != 1 or k > 15 or 2 * p > k:
+                continue
+            setattr(parent, name, MaxPool2d(k, s, p))
+            n += 1
+    return n
+
+
 def use_channels_last_padding(module: nn.Module) -> int:
     """Replace every nn.ReflectionPad2d inside ``module`` (the reference's Conv3x3 blocks) by ReflectionPad2d above;
     returns how many were replaced.  Call it next to ``module.to(memory_format=torch.channels_last)``."""

@@ -85,6 +85,18 @@ int md2_reflection_pad2d_forward(int N, int C, int H, int W, int pad_l, int pad_
 int md2_reflection_pad2d_backward(int N, int C, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b,
                                   int channels_last, const float* g_out, float* g_in, md2_stream_t stream);
 
+/* nn.MaxPool2d(kernel, stride, padding) (dilation 1, ceil_mode False) of the ResNet encoders
+ * (model_layer/depth_encoder.py:29: 3, 2, 1) on channels-last buffers: in [N,H,W,C] -> out [N,Ho,Wo,C] with
+ * Ho = (H + 2*padding - kernel) / stride + 1, bit-identical to ATen (ties go to the first element in row-major window
+ * order, NaN wins).  `winner` [N,Ho,Wo,C] uint8 receives each maximum's offset inside its window (dy*kernel + dx) and is
+ * what the backward reads: g_in [N,H,W,C] is overwritten with the sum of the output gradients whose winner the element
+ * is - a gather in a fixed order (ATen: atomics into a zero-filled buffer, 8-byte indices).  kernel <= 15,
+ * 2*padding <= kernel. */
+int md2_maxpool2d_nhwc_forward(int N, int C, int H, int W, int kernel, int stride, int padding, const float* in,
+                               float* out, uint8_t* winner, md2_stream_t stream);
+int md2_maxpool2d_nhwc_backward(int N, int C, int H, int W, int kernel, int stride, int padding, const float* g_out,
+                                const uint8_t* winner, float* g_in, md2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

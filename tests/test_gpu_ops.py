@@ -334,3 +334,76 @@ def test_reflection_pad2d_rejects_bad_input_and_swaps_into_modules():
     assert M.use_channels_last_padding(net) == 2
     assert isinstance(net[0], M.ReflectionPad2d) and net[2][0].padding == (1, 0, 2, 1)
     assert torch.equal(net(x), ref)
+
+
+# ----------------------------------------------------------------------------- MaxPool2d (encoder stem)
+@pytest.mark.parametrize("shape,k,s,p,kind", [
+    ((2, 64, 24, 40), 3, 2, 1, "relu"),        # the encoders' stem (depth_encoder.py:29) on post-ReLU data: many ties
+    ((3, 6, 7, 9), 3, 2, 1, "randn"),          # C % 4 != 0 (scalar path), odd sizes
+    ((1, 8, 5, 5), 2, 2, 0, "ties"),           # every window is one repeated value
+    ((2, 4, 9, 11), 3, 1, 1, "randn"),         # stride 1: an element is in nine windows
+    ((1, 4, 6, 6), 5, 3, 2, "nan"),            # NaN and isolated -inf inputs
+    ((12, 64, 96, 320), 3, 2, 1, "relu"),      # the real stem at batch 12
+])
+def test_maxpool2d_nhwc_matches_aten(shape, k, s, p, kind):
+    """Values bit-identical to nn.MaxPool2d; the winner of every window is ATen's (compared through the gradient: with
+    integer-valued output gradients every summation order is exact, so the input gradients must be bit-identical)."""
+    import md2_b200.modules as M
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(*shape, generator=g)
+    if kind == "relu":
+        x = x.clamp_min(0)
+    elif kind == "ties":
+        x = torch.round(x)
+        x = x[:, :, :1, :1].expand(shape).clone()
+    elif kind == "nan":
+        x[0, 0, 2, 2] = float("nan")
+        x[0, 2, 1, 1] = float("-inf")
+        x[0, 2, 4, 3] = float("-inf")
+    x = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ref = torch.nn.MaxPool2d(k, s, p)(xa)
+    ours = M.MaxPool2d(k, s, p)(xb)
+    assert ours.shape == ref.shape and ours.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(torch.nan_to_num(ours, nan=123.0), torch.nan_to_num(ref, nan=123.0))
+    go = torch.randint(-8, 9, ref.shape, generator=g).float().to(DEV).contiguous(memory_format=torch.channels_last)
+    ref.backward(go)
+    ours.backward(go)
+    assert torch.equal(xb.grad, xa.grad)
+    assert xb.grad.is_contiguous(memory_format=torch.channels_last)
+
+
+def test_maxpool2d_window_without_a_maximum():
+    """A window that holds only -inf has no element greater than the running maximum: the gradient goes to the first
+    in-bounds element, as in ATen's CPU and NCHW CUDA kernels (its NHWC CUDA kernel sends it to element (0, 0) of the
+    plane instead - a quirk this kernel does not copy; unreachable behind a ReLU)."""
+    import md2_b200.modules as M
+    x = torch.full((1, 4, 6, 6), float("-inf"))
+    x[0, 3] = torch.arange(36.0).view(6, 6)
+    go = torch.arange(1.0, 1 + 4 * 3 * 3).view(1, 4, 3, 3)
+    xa = x.clone().requires_grad_(True)
+    torch.nn.MaxPool2d(3, 2, 1)(xa).backward(go)                                   # CPU reference
+    xb = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    out = M.MaxPool2d(3, 2, 1)(xb)
+    out.backward(go.to(DEV))
+    assert torch.equal(xb.grad.cpu(), xa.grad)
+
+
+def test_maxpool2d_swaps_into_the_encoder_and_rejects_bad_input():
+    import torchvision
+    import md2_b200.modules as M
+    enc = torchvision.models.resnet18(weights=None).to(DEV).to(memory_format=torch.channels_last).eval()
+    x = torch.rand(2, 3, 64, 96, device=DEV).contiguous(memory_format=torch.channels_last)
+    stem = lambda m: m.maxpool(m.relu(m.bn1(m.conv1(x))))
+    with torch.no_grad():
+        ref = stem(enc)
+        assert M.use_channels_last_pooling(enc) == 1 and isinstance(enc.maxpool, M.MaxPool2d)
+        assert torch.equal(stem(enc), ref)
+    with pytest.raises(RuntimeError):
+        M.MaxPool2d(3, 2, 1)(x.cpu())
+    with pytest.raises(RuntimeError):
+        M.MaxPool2d(3, 2, 1)(x.double())
+    with pytest.raises(ValueError):
+        M.MaxPool2d(3, 2, 2)                                  # padding > kernel / 2, like torch
+    with pytest.raises(RuntimeError):
+        M.MaxPool2d(5, 1, 0)(torch.rand(1, 4, 3, 3, device=DEV))   # window larger than the image

@@ -48,6 +48,11 @@ def test_operator_entry_points_validate_without_gpu(lib):
     assert lib.md2_reflection_pad2d_forward(1, 4, 4, 4, 1, 1, 1, 1, 1, null, one, null) == cabi.MD2_ERR_NULL
     assert lib.md2_reflection_pad2d_backward(0, 4, 4, 4, 1, 1, 1, 1, 1, one, one, null) == cabi.MD2_ERR_SHAPE
     assert lib.md2_reflection_pad2d_backward(1, 4, 4, 4, 1, 1, 1, 1, 0, one, null, null) == cabi.MD2_ERR_NULL
+    assert lib.md2_maxpool2d_nhwc_forward(1, 4, 4, 4, 3, 2, 2, one, one, one, null) == cabi.MD2_ERR_SHAPE     # 2p > k
+    assert lib.md2_maxpool2d_nhwc_forward(1, 4, 2, 2, 5, 1, 0, one, one, one, null) == cabi.MD2_ERR_SHAPE     # window > image
+    assert lib.md2_maxpool2d_nhwc_forward(1, 4, 8, 8, 3, 2, 1, one, one, null, null) == cabi.MD2_ERR_NULL
+    assert lib.md2_maxpool2d_nhwc_backward(1, 4, 8, 8, 3, 0, 1, one, one, one, null) == cabi.MD2_ERR_SHAPE
+    assert lib.md2_maxpool2d_nhwc_backward(1, 4, 8, 8, 3, 2, 1, null, one, one, null) == cabi.MD2_ERR_NULL
     assert lib.md2_reprojection_forward(1, 2, 8, one, one, one, null) == cabi.MD2_ERR_SHAPE
     assert lib.md2_smooth_forward(1, 8, 8, one, one, null, one, null) == cabi.MD2_ERR_NULL
 

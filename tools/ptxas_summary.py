@@ -3,7 +3,7 @@ import re, subprocess, sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import md2_b200.build as b
-srcs = [os.path.join(b.CSRC, f) for f in ("md2_abi.cu", "md2_l1.cu", "md2_metrics.cu", "md2_pipeline.cu", "md2_jitter.cu", "md2_pad.cu")]
+srcs = [os.path.join(b.CSRC, f) for f in ("md2_abi.cu", "md2_l1.cu", "md2_metrics.cu", "md2_pipeline.cu", "md2_jitter.cu", "md2_pad.cu", "md2_pool.cu")]
 extra = sys.argv[1:]
 r = subprocess.run([b.NVCC] + b.NVCC_FLAGS + ["-Xptxas", "-v"] + extra + srcs + ["-o", b.LIB], capture_output=True, text=True)
 if r.returncode != 0:

@@ -141,8 +141,10 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_
         if loss_impl == "fused" and os.environ.get("MD2_STOCK_PAD", "0") != "1":
             # ATen's reflection pad only knows NCHW: every Conv3x3 would pay layout copies around it, forward and
             # backward.  md2_b200.modules.ReflectionPad2d is the same operator (bit-identical) that keeps NHWC tensors NHWC.
-            from md2_b200.modules import use_channels_last_padding
+            from md2_b200.modules import use_channels_last_padding, use_channels_last_pooling
             use_channels_last_padding(nets)
+            if os.environ.get("MD2_STOCK_POOL", "0") != "1":   # same for the encoders' max-pool (gather backward)
+                use_channels_last_pooling(nets)
     # With --graph the DDP wrapper is not used: md2_b200.trainer.GraphedTrainStep keeps the gradients in one flat,
     # bucketed buffer and overlaps the bucket all-reduces with the backward pass inside the captured step (comm =
     # "captured"), or runs them eagerly between a forward+backward graph and an optimizer graph (comm = "eager").

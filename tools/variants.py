@@ -7,7 +7,7 @@ tools/bench_variants.py times every one of them on the benchmark configuration."
 import os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "digging-into-self-supervised-monocular-depth-estimation_b200", "csrc")
-SRCS = [os.path.join(CSRC, f) for f in ("md2_abi.cu", "md2_l1.cu", "md2_metrics.cu", "md2_pipeline.cu", "md2_jitter.cu", "md2_pad.cu")]
+SRCS = [os.path.join(CSRC, f) for f in ("md2_abi.cu", "md2_l1.cu", "md2_metrics.cu", "md2_pipeline.cu", "md2_jitter.cu", "md2_pad.cu", "md2_pool.cu")]
 OUT = os.path.join(ROOT, "build", "variants")
 os.makedirs(OUT, exist_ok=True)
 procs = []
