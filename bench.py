@@ -564,7 +564,8 @@ def train_step_leg(dev, world, local, steps=12, warmup=4):
     return {"metric": "train_images_per_sec", "value": imgs * world / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
             "steps": steps, "warmup": warmup, "n_gpus": world, "final_loss": final,
             "mode": "fused loss, channels-last networks with md2_b200.modules.ReflectionPad2d (NHWC-preserving, "
-                    "bit-identical) in the decoder's Conv3x3, cuDNN autotuner on (as the reference sets it, "
+                    "bit-identical) in the decoder's Conv3x3 and md2_b200.modules.MaxPool2d in the encoder stems, cuDNN "
+                    "autotuner on (as the reference sets it, "
                     "model_utility.py:327), fused Adam, whole step one CUDA graph, 6 gradient buckets all-reduced inside "
                     "the graph (md2_b200.trainer.GraphedTrainStep)",
             "config": "ResNet-18 depth + separate ResNet-18 pose net, batch 12 per GPU, 192x640, frame_ids [0,-1,1], "
