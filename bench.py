@@ -532,7 +532,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def train_step_leg(dev, world, local, steps=12, warmup=4):
+def train_step_leg(dev, world, local, steps=30, warmup=8):
     """BASELINE.json configs[2] at this N: full mono training step (ResNet-18 depth + separate pose network on stock
     PyTorch / cuDNN, channels-last, fused loss, Adam), batch 12 per GPU, replayed as one CUDA graph by
     md2_b200.trainer.GraphedTrainStep with the bucket all-reduces captured inside it.  Every rank returns the dict."""
