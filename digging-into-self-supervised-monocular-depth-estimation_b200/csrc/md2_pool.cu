@@ -11,7 +11,7 @@
 //   backward  a gather: every input element looks at the <= ceil(k/s)^2 windows that contain it and adds the output
 //             gradients of those whose winner it is - no atomics, no zero fill, fixed order.
 // Values are bit-identical to nn.MaxPool2d; gradients are equal up to the order of at most four additions.
-// NHWC only (float4 when C % 4 == 0): an NCHW caller keeps ATen's operator (the Python wrapper raises).
+// NHWC only (float4 when C % 4 == 0); the Python wrapper converts a tensor that is not channels-last first.
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -113,6 +113,57 @@ __global__ void __launch_bounds__(256) maxpool_bwd(const float* __restrict__ g_o
   else g_in[i] = acc[0];
 }
 
+// The encoders' case (3, 2, 1) with float4 channels: one thread per 2 x 2 input block.  Row 2i lies in window row i only
+// (offset 1), row 2i+1 in window rows i (offset 2) and i+1 (offset 0), the same along x: the four windows (i..i+1) x
+// (j..j+1) are read once and serve four elements, each summed in the same window order as maxpool_bwd.
+__global__ void __launch_bounds__(256) maxpool_bwd_3x3s2(const float* __restrict__ g_out, const uint8_t* __restrict__ win,
+                                                          float* __restrict__ g_in, const __grid_constant__ PoolShape q) {
+  const int cv = q.C / 4, Wb = (q.W + 1) / 2, Hb = (q.H + 1) / 2;
+  const unsigned t = blockIdx.y * 256u + threadIdx.x;
+  if (t >= (unsigned)(Wb * cv)) return;
+  const int j = t / cv, c = (t - j * cv) * 4;
+  const unsigned n = blockIdx.x / Hb;
+  const int i = blockIdx.x - n * Hb;
+  float4 g[2][2];
+  uchar4 w[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int yo = i + a, xo = j + b;
+      if (yo < q.Ho && xo < q.Wo) {
+        const size_t o = (((size_t)n * q.Ho + yo) * q.Wo + xo) * q.C + c;
+        w[a][b] = __ldg(reinterpret_cast<const uchar4*>(win + o));
+        g[a][b] = __ldg(reinterpret_cast<const float4*>(g_out + o));
+      } else {
+        w[a][b] = make_uchar4(255, 255, 255, 255);  // no such window
+        g[a][b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  // element (2i + r, 2j + u) sits at offset (oy(r, a), ox(u, b)) of window (i + a, j + b): r = 0 -> a = 0 only, dy = 1;
+  // r = 1 -> a = 0 with dy = 2, a = 1 with dy = 0
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int y = 2 * i + r, x = 2 * j + u;
+      if (y >= q.H || x >= q.W) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a <= r; ++a)
+#pragma unroll
+        for (int b = 0; b <= u; ++b) {
+          const int dy = r == 0 ? 1 : (a == 0 ? 2 : 0), dx = u == 0 ? 1 : (b == 0 ? 2 : 0);
+          const unsigned char me = (unsigned char)(dy * 3 + dx);
+          if (w[a][b].x == me) acc.x += g[a][b].x;
+          if (w[a][b].y == me) acc.y += g[a][b].y;
+          if (w[a][b].z == me) acc.z += g[a][b].z;
+          if (w[a][b].w == me) acc.w += g[a][b].w;
+        }
+      *reinterpret_cast<float4*>(g_in + (((size_t)n * q.H + y) * q.W + x) * q.C + c) = acc;
+    }
+}
+
 static int check_pool(int N, int C, int H, int W, int k, int s, int p, PoolShape* q) {
   if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || k <= 0 || s <= 0 || p < 0) return MD2_ERR_SHAPE;
   if (k > 15 || 2 * p > k) return MD2_ERR_SHAPE;  // offsets fit a byte; torch: "pad should be at most half of kernel size"
@@ -154,6 +205,13 @@ int md2_maxpool2d_nhwc_backward(int N, int C, int H, int W, int kernel, int stri
   if (!g_out || !winner || !g_in) return MD2_ERR_NULL;
   const NvtxRange range("md2_maxpool2d_nhwc_backward");
   const bool vec = (C % 4 == 0) && ((((uintptr_t)g_out | (uintptr_t)g_in) & 15) == 0) && (((uintptr_t)winner & 3) == 0);
+  if (vec && kernel == 3 && stride == 2 && padding == 1) {  // the encoders' stem
+    const dim3 grid2((unsigned)(N * ((H + 1) / 2)), (unsigned)((((W + 1) / 2) * (C / 4) + 255) / 256));
+    if (grid2.y > 65535) return MD2_ERR_SHAPE;
+    maxpool_bwd_3x3s2<<<grid2, 256, 0, (cudaStream_t)stream>>>(g_out, winner, g_in, q);
+    const cudaError_t e2 = cudaGetLastError();
+    return e2 == cudaSuccess ? 0 : (int)e2;
+  }
   const int row_vectors = q.W * (vec ? C / 4 : C);
   const dim3 grid((unsigned)(N * q.H), (unsigned)((row_vectors + 255) / 256));
   if (grid.y > 65535) return MD2_ERR_SHAPE;
