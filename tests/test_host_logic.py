@@ -94,3 +94,38 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert not pat.search(src), f
+
+
+def test_channels_last_module_swaps_are_host_logic():
+    """md2_b200.modules.use_channels_last_padding / _pooling only rewire modules (no GPU needed); the swapped modules
+    refuse host tensors - there is no CPU path behind them."""
+    import torch
+    import torch.nn as nn
+    import md2_b200.modules as M
+
+    class Conv3x3(nn.Module):                       # shaped like model_layer/depth_decoder.py:36-50
+        def __init__(self):
+            super().__init__()
+            self.pad = nn.ReflectionPad2d(1)
+            self.conv = nn.Conv2d(4, 4, 3)
+
+    net = nn.ModuleDict({"a": Conv3x3(), "b": nn.Sequential(Conv3x3(), nn.ZeroPad2d(1)),
+                         "pool": nn.MaxPool2d(3, 2, 1), "pool_ceil": nn.MaxPool2d(3, 2, 1, ceil_mode=True),
+                         "pool_rect": nn.MaxPool2d((3, 2), 2), "pool_dil": nn.MaxPool2d(3, 2, 1, dilation=2)})
+    assert M.use_channels_last_padding(net) == 2
+    assert isinstance(net["a"].pad, M.ReflectionPad2d) and net["a"].pad.padding == (1, 1, 1, 1)
+    assert isinstance(net["b"][1], nn.ZeroPad2d)                     # only reflection pads are replaced
+    assert M.use_channels_last_padding(net) == 0                     # idempotent
+    assert M.use_channels_last_pooling(net) == 1
+    assert isinstance(net["pool"], M.MaxPool2d) and (net["pool"].kernel_size, net["pool"].stride, net["pool"].padding) == (3, 2, 1)
+    for k in ("pool_ceil", "pool_rect", "pool_dil"):                 # unsupported variants keep ATen's operator
+        assert type(net[k]) is nn.MaxPool2d
+    x = torch.zeros(1, 4, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net["a"].pad(x)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net["pool"](x)
+    with pytest.raises(ValueError):
+        M.ReflectionPad2d((1, 2, 3))
+    with pytest.raises(ValueError):
+        M.MaxPool2d(3, 2, 2)
