@@ -35,12 +35,12 @@ def _run(make, n_steps, graph):
     return losses, flat
 
 
-def _tiny_factory():
+def _tiny_factory(branch_streams=False):
     import train_step as ts
     from md2_b200 import functional as F_
     from md2_b200.compute import compute
     B, H, W, fids = 2, 64, 96, [0, -1, 1]
-    nets = ts.MonoNets().to(DEV)
+    nets = ts.MonoNets(branch_streams=branch_streams).to(DEV)
     cfg = SimpleNamespace(frame_ids=fids, scales=range(4), height=H, width=W, min_depth=0.1, max_depth=100.0,
                           pose_type="separate", use_automasking=True, disp_smoothness=1e-3)
     comp = compute(cfg, DEV)
@@ -62,6 +62,21 @@ def test_graph_replays_equal_eager_steps():
     for a, b in zip(le, lg):
         assert a == pytest.approx(b, rel=2e-4), (le, lg)
     assert float((pe - pg).abs().max()) <= 2e-5
+
+
+def test_branch_streams_in_the_graph_equal_the_single_stream_eager_step():
+    """md2_b200.trainer.BranchStreams: depth and pose branches captured as parallel branches of the step's graph (forward
+    and backward on two streams) give the losses and parameters of the plain single-stream eager loop."""
+    le, pe = _run(_tiny_factory, 4, graph=False)
+    lg, pg = _run(lambda: _tiny_factory(branch_streams=True), 4, graph=True)
+    for a, b in zip(le, lg):
+        assert a == pytest.approx(b, rel=2e-4), (le, lg)
+    assert float((pe - pg).abs().max()) <= 2e-5
+    # and eagerly, without a graph
+    ls, ps = _run(lambda: _tiny_factory(branch_streams=True), 4, graph=False)
+    for a, b in zip(le, ls):
+        assert a == pytest.approx(b, rel=2e-4), (le, ls)
+    assert float((pe - ps).abs().max()) <= 2e-5
 
 
 def _reference_factory():

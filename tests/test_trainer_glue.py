@@ -126,3 +126,17 @@ def test_two_gloo_ranks_match_distributed_data_parallel():
         assert a == pytest.approx(b, rel=1e-5)
     assert ret["param_err"] <= 1e-5
     assert ret["bn_err"] <= 1e-6
+
+
+def test_branch_streams_without_cuda_run_in_order():
+    """md2_b200.trainer.BranchStreams on a host without CUDA (or disabled): the callables run sequentially, results in
+    argument order."""
+    from md2_b200.trainer import BranchStreams
+    log = []
+    br = BranchStreams(enabled=torch.cuda.is_available())
+    out = br(lambda: log.append("main") or {"a": torch.ones(2)}, lambda: log.append("side1") or [torch.zeros(1)],
+             lambda: log.append("side2") or 3)
+    assert isinstance(out, list) and len(out) == 3 and out[2] == 3 and torch.equal(out[0]["a"], torch.ones(2))
+    assert sorted(log) == ["main", "side1", "side2"]
+    assert BranchStreams(enabled=False)(lambda: 1, lambda: 2) == [1, 2]
+    assert BranchStreams()(lambda: 7) == [7]

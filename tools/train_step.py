@@ -96,23 +96,37 @@ class PoseDecoder(nn.Module):
 class MonoNets(nn.Module):
     """The four networks behind one module so that a single DDP wrapper covers them."""
 
-    def __init__(self, layers=18):
+    def __init__(self, layers=18, branch_streams=None):
         super().__init__()
         self.enc = Encoder(1, layers)
         self.dec = DepthDecoder(self.enc.ch)
         self.pose_enc = Encoder(2, layers)
         self.pose_dec = PoseDecoder(self.pose_enc.ch[-1])
+        from md2_b200.trainer import BranchStreams
+        self.branch_streams = (os.environ.get("MD2_BRANCH_STREAMS", "1") == "1") if branch_streams is None else bool(branch_streams)
+        self._branches = BranchStreams()
+
+    def _pose(self, inputs, f):
+        pair = [inputs[("color_aug", f, 0)], inputs[("color_aug", 0, 0)]] if f < 0 else \
+               [inputs[("color_aug", 0, 0)], inputs[("color_aug", f, 0)]]
+        aa, tr = self.pose_dec(self.pose_enc(torch.cat(pair, 1))[-1])
+        return aa[:, 0].contiguous(), tr[:, 0].contiguous()
 
     def forward(self, inputs, frame_ids):
-        outputs = self.dec(self.enc(inputs[("color_aug", 0, 0)]))
-        for f in frame_ids[1:]:
-            if f == "s":   # the stereo baseline is data (inputs["stereo"]), no pose network
-                continue
-            pair = [inputs[("color_aug", f, 0)], inputs[("color_aug", 0, 0)]] if f < 0 else \
-                   [inputs[("color_aug", 0, 0)], inputs[("color_aug", f, 0)]]
-            aa, tr = self.pose_dec(self.pose_enc(torch.cat(pair, 1))[-1])
-            outputs[("axisangle", f)] = aa[:, 0].contiguous()
-            outputs[("translation", f)] = tr[:, 0].contiguous()
+        x0 = inputs[("color_aug", 0, 0)]
+        mono = [f for f in frame_ids[1:] if f != "s"]   # the stereo baseline is data (inputs["stereo"]), no pose network
+        if not (self.branch_streams and x0.is_cuda and mono):
+            outputs = self.dec(self.enc(x0))
+            for f in mono:
+                outputs[("axisangle", f)], outputs[("translation", f)] = self._pose(inputs, f)
+            return outputs
+        # The depth network and the pose network do not depend on each other until the loss: md2_b200.trainer.
+        # BranchStreams runs the pose branch on a side stream (a parallel branch of the captured graph, forward and
+        # backward).  The pairs stay sequential inside that branch: they share the pose network's BatchNorm buffers.
+        outputs, poses = self._branches(lambda: self.dec(self.enc(x0)),
+                                        lambda: {f: self._pose(inputs, f) for f in mono})
+        for f, (aa, tr) in poses.items():
+            outputs[("axisangle", f)], outputs[("translation", f)] = aa, tr
         return outputs
 
 
@@ -135,7 +149,9 @@ def make_step(loss_impl, B, H, W, frame_ids, device, ddp, graph=False, channels_
     from types import SimpleNamespace
     # the reference switches cuDNN's autotuner on (model_utility.py:327-328); shapes are static, so it pays once
     torch.backends.cudnn.benchmark = os.environ.get("MD2_CUDNN_BENCHMARK", "1") == "1"
-    nets = MonoNets(layers).to(device)
+    # depth and pose branches on two streams (md2_b200.trainer.BranchStreams) in the graphed step; the eager /
+    # DistributedDataParallel arms keep the reference's single-stream order
+    nets = MonoNets(layers, branch_streams=bool(graph) and os.environ.get("MD2_BRANCH_STREAMS", "1") == "1").to(device)
     if channels_last:   # NHWC activations for the cuDNN convolutions (precision-neutral); the loss inputs stay NCHW
         nets = nets.to(memory_format=torch.channels_last)
         if loss_impl == "fused" and os.environ.get("MD2_STOCK_PAD", "0") != "1":
