@@ -79,7 +79,7 @@ def test_branch_streams_in_the_graph_equal_the_single_stream_eager_step():
     assert float((pe - ps).abs().max()) <= 2e-5
 
 
-def _reference_factory():
+def _reference_factory(two_streams=False):
     from oracle import ref_loader as RL
     import train_step as ts
     from md2_b200.compute import compute as FusedCompute
@@ -105,10 +105,18 @@ def _reference_factory():
     fused = FusedCompute(opt, DEV)             # ... and this package's image2warping / compute_loss
     fused.base_seed = 99
 
+    from md2_b200.trainer import BranchStreams
+    branches = BranchStreams(enabled=two_streams)
+
     def batch_process(inputs):                 # model_train.py:90-96 with the two loss calls swapped
-        outputs = {}
-        inputs, outputs = ref_compute.forward_depth(inputs, outputs, setting)
-        inputs, outputs = ref_compute.forward_pose(inputs, outputs, setting)
+        if two_streams:                        # depth and pose networks on two streams
+            depth_out, pose_out = branches(lambda: ref_compute.forward_depth(inputs, {}, setting)[1],
+                                           lambda: ref_compute.forward_pose(inputs, {}, setting)[1])
+            outputs = {**depth_out, **pose_out}
+        else:
+            outputs = {}
+            inputs, outputs = ref_compute.forward_depth(inputs, outputs, setting)
+            inputs, outputs = ref_compute.forward_pose(inputs, outputs, setting)
         inputs, outputs = fused.image2warping(inputs, outputs, setting)
         return fused.compute_loss(inputs, outputs, setting)
     batches = [ts.synthetic_batch(B, H, W, fids, s, torch.device(DEV)) for s in range(2)]
@@ -125,6 +133,11 @@ def test_graphed_step_over_the_reference_trainer_objects():
     for a, b in zip(le, lg):
         assert a == pytest.approx(b, rel=2e-4), (le, lg)
     assert float((pe - pg).abs().max()) <= 2e-5
+    # the same objects with forward_depth / forward_pose on two streams inside the captured step
+    l2, p2 = _run(lambda: _reference_factory(two_streams=True), 3, graph=True)
+    for a, b in zip(le, l2):
+        assert a == pytest.approx(b, rel=2e-4), (le, l2)
+    assert float((pe - p2).abs().max()) <= 2e-5
 
 
 def test_lr_schedule_reaches_the_captured_optimizer():
