@@ -9,7 +9,7 @@ reference's graph, model_train.py:68), so nothing is recomputed or re-read.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 

@@ -40,7 +40,7 @@ exercise, and a drop-in for DistributedDataParallel when graphs are not wanted.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Iterable, List, Optional, Union
+from typing import Callable, Dict, Iterable, List, Union
 
 import torch
 import torch.distributed as dist
